@@ -1,0 +1,158 @@
+/*
+ * panib200.h -- C ABI of libpanib200.so, the B200 (sm_100a) engine behind pyani-plus's
+ * `sourmash` method.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * What it replaces.  In the reference the arithmetic of this path is done by two external
+ * commands spawned from Python:
+ *   sourmash scripts singlesketch -I DNA -p k=K,scaled=S    pyani_plus/methods/sourmash.py:67-83
+ *   sourmash scripts manysearch   -m DNA -t 0               pyani_plus/methods/sourmash.py:184-200
+ * (called from prepare_genomes :34-84 and compute_sourmash_tile :147-206, driven by
+ * private_cli.prepare private_cli.py:714-754 and private_cli.compute_sourmash :1803-1902).
+ * The entry points below are what a reference-side binding (ctypes) would
+ * call instead of those two subprocesses.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative PANIB_E_* code on failure; the text of the
+ *    last failure on the calling thread is available from panib_last_error();
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all device work is
+ *    enqueued on it and the call returns without synchronising unless stated otherwise;
+ *  - pointers named d_* are device pointers (the caller owns all memory -- the Python host
+ *    allocates them as torch tensors), h_* are host pointers (pinned for async copies);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Device data layout
+ *  base stream   All genomes of a batch are laid out in one stream of bases cut into tiles of
+ *                PANIB_TILE_BASES positions.  Genome g owns tiles [tile_off[g], tile_off[g+1]);
+ *                its records are written back to back with ONE invalid separator base between
+ *                records, and the rest of its last tile is invalid padding (at least one base),
+ *                so no k-mer window can span two records or two genomes.  The stream is followed
+ *                by one extra all-invalid tile (halo for the last real tile).
+ *                ASCII form: 1 byte per base ('N' or any non-ACGT byte = invalid).
+ *                Packed form: 2 bits per base, 16 bases per uint32, base i of a word at bits
+ *                [2i+1:2i], A=0 C=1 G=2 T=3; plus a validity mask, 1 bit per base, 32 bases per
+ *                uint32, bit set = invalid.
+ *  sketch table  Row g (row_stride uint64 slots, row_stride = max nb[g] * PANIB_BUCKET_SLOTS)
+ *                first serves as nb[g] value-range buckets of open-addressing hash sets while
+ *                k-mers are hashed, and is then sorted / de-duplicated / compacted IN PLACE so
+ *                that row g holds counts[g] ascending distinct hashes starting at slot 0.
+ *  overlap       ov[q * ld + s] = |sketch_q n sketch_s| as uint32.
+ */
+#ifndef PANIB200_H
+#define PANIB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PANIB_API __attribute__((visibility("default")))
+#else
+#define PANIB_API
+#endif
+
+#define PANIB_VERSION_STRING "0.1.0"
+#define PANIB_TILE_BASES 4096      /* k-mer start positions per tile / per CTA of the sketch kernel */
+#define PANIB_BUCKET_SLOTS 1024    /* uint64 slots per value-range bucket of a sketch-table row    */
+#define PANIB_MAX_FAST_K 32        /* k handled by the register-resident kernel (k=21,31 built)     */
+#define PANIB_MAX_K 255
+
+#define PANIB_OK 0
+#define PANIB_E_CUDA (-1)          /* a CUDA runtime call or kernel launch failed                   */
+#define PANIB_E_ARG (-2)           /* invalid argument                                             */
+#define PANIB_E_NODEVICE (-3)      /* no CUDA device: this library has no CPU path                  */
+
+/* bits of the device status word written by kernels (d_status, int32, caller zero-initialises) */
+#define PANIB_ST_BUCKET_OVERFLOW 1 /* a sketch bucket filled up: re-run with more buckets           */
+#define PANIB_ST_SEGMENT_OVERFLOW 2/* a pairwise segment exceeded seg_cap: re-run with more cells    */
+
+/* ---- library ------------------------------------------------------------------------------ */
+PANIB_API const char *panib_version(void);                    /* "0.1.0 sm_100a ..."                        */
+PANIB_API int panib_last_error(char *buf, size_t n);           /* copies the last error text; returns length */
+PANIB_API int panib_device_count(void);                        /* 0 when no usable CUDA device               */
+PANIB_API uint64_t panib_launch_count(void);                   /* kernels launched by this library so far    */
+
+/* max_hash of a FracMinHash `scaled`: 0->0, 1->2^64-1, else (uint64)(2^64 / (double)scaled).
+ * Replaces sourmash's max_hash_for_scaled; pinned by the "max_hash" field of the fixture .sig files. */
+PANIB_API uint64_t panib_max_hash(uint64_t scaled);
+
+/* Bucket plan for one genome with n_kmers candidate windows: number of buckets nb (>=1) and the
+ * multiplier bmul with bucket(h) = mulhi64(h, bmul) (monotone in h, < nb for h <= max_hash). */
+PANIB_API int panib_plan_buckets(int64_t n_kmers, uint64_t scaled, double slack, int32_t *nb, uint64_t *bmul);
+
+/* ---- stage 0: ASCII base stream -> packed 2-bit + validity mask --------------------------- */
+/* n_bases must be a multiple of 32.  Upper-cases; any byte other than A,C,G,T is invalid. */
+PANIB_API int panib_pack_ascii(const uint8_t *d_ascii, int64_t n_bases, uint32_t *d_packed, uint32_t *d_mask,
+                     void *stream);
+
+/* ---- stage 1 (kernel K1): FracMinHash sketching -- replaces `sourmash scripts singlesketch` -- */
+/* d_packed/d_mask: stream of (n_tiles+1) tiles.  d_tile_off[n_genomes+1]: int64 tile offsets.
+ * d_nb[n_genomes], d_bmul[n_genomes]: bucket plan.  d_table: n_genomes*row_stride uint64, need not be
+ * initialised.  d_flags[n_genomes]: int32 scratch.  On completion (stream order) row g holds the
+ * sorted distinct hashes h = murmur3_x64_128(canonical k-mer, seed).h1 with 0 < h <= max_hash and
+ * d_counts[g] (int32) their number.  d_status: int32, PANIB_ST_* bits are OR-ed in.            */
+PANIB_API int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
+                        int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                        const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                        int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
+                        void *stream);
+
+/* The two halves of panib_sketch_stream, exposed for profiling / benchmarking. */
+PANIB_API int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
+                           int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                           const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                           int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream);
+PANIB_API int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int64_t n_genomes, const int32_t *d_nb,
+                          int32_t *d_counts, const int32_t *d_flags, void *stream);
+
+/* Host-buffer form (what a caller holding FASTA bytes uses): copies the pinned ASCII stream
+ * host->device on `stream`, packs it and sketches it.  d_ascii is device scratch of n_bases bytes,
+ * n_bases = (n_tiles+1)*PANIB_TILE_BASES. */
+PANIB_API int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
+                            uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
+                            int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                            const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                            int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
+                            void *stream);
+
+/* ---- stage 2 (kernel K2): all-vs-all sorted-sketch intersection -- replaces `manysearch` ---- */
+/* Queries are rows of (d_q_rows, d_q_counts, q_stride), subjects rows of (d_s_rows, ...); they may be
+ * the same table.  symmetric != 0 requires the same table and computes only q < s, mirroring the
+ * result and writing the diagonal (= sketch size).  n_cells / seg_cap / idx_buckets choose the
+ * shared-memory segmentation; pass 0 for all three to let the library choose from
+ * max_count (the largest sketch size).  d_fence: int32 scratch of (nq+ns)*(n_cells+1) entries
+ * (unused when n_cells == 1, may be NULL).  d_ov: uint32 [nq x ld_ov], fully overwritten.
+ * Multi-GPU: rank r of world w processes the work items it owns (item % w == r) and leaves the
+ * rest of d_ov zero, so the ranks' matrices sum to the full result. */
+PANIB_API int panib_intersect(const uint64_t *d_q_rows, const int32_t *d_q_counts, int64_t q_stride, int64_t nq,
+                    const uint64_t *d_s_rows, const int32_t *d_s_counts, int64_t s_stride, int64_t ns,
+                    int symmetric, uint64_t max_hash, int64_t max_count, int n_cells, int seg_cap,
+                    int idx_buckets, int32_t *d_fence, uint32_t *d_ov, int64_t ld_ov, int rank, int world,
+                    int32_t *d_status, void *stream);
+/* Size (in int32 entries) of the d_fence scratch panib_intersect needs for these arguments. */
+PANIB_API int64_t panib_intersect_fence_entries(int64_t nq, int64_t ns, uint64_t max_hash, int64_t max_count,
+                                      int n_cells, int seg_cap);
+
+/* ---- stage 3: containment -> ANI ------------------------------------------------------------ */
+/* identity[q,s] = max(ani(ov/|Q|), ani(ov/|S|)), cov_query[q,s] = ani(ov/|Q|),
+ * ani(c) = 0 if c==0, 1 if c==1, else 1-(1-c^(1/k)); NaN where branchwater prints no row (ov==0).
+ * pyani-plus mapping: private_cli.py:1875-1887.  Device form uses CUDA's double pow (<= 2 ulp);
+ * the host form uses libm pow and is the one the drop-in CLI path uses (repr-exact floats). */
+PANIB_API int panib_ani_device(const uint32_t *d_ov, int64_t ld_ov, const int32_t *d_q_counts, int64_t nq,
+                     const int32_t *d_s_counts, int64_t ns, int k, double *d_identity,
+                     double *d_cov_query, void *stream);
+PANIB_API int panib_ani_host(const uint32_t *h_ov, int64_t ld_ov, const int32_t *h_q_counts, int64_t nq,
+                   const int32_t *h_s_counts, int64_t ns, int k, double *h_identity, double *h_cov_query);
+
+/* ---- synthetic genomes (BASELINE.json configs 2-5) ---------------------------- */
+/* Writes genomes g0..g0+n_genomes-1 (each `length` bases, one record) into an ASCII base stream
+ * with the layout above: genome i at tile i*tiles_per_genome, tiles_per_genome = length/TILE + 1. */
+PANIB_API int panib_synth_ascii(uint64_t seed, int64_t g0, int64_t n_genomes, int64_t length, uint8_t *d_ascii,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANIB200_H */

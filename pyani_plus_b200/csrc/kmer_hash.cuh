@@ -1,0 +1,233 @@
+// kmer_hash.cuh -- per-thread core of the sketch kernel (K1): canonical k-mers of a 2-bit packed
+// base stream -> MurmurHash3_x64_128(seed).h1 over the ASCII bytes of the canonical k-mer, exactly
+// as `sourmash scripts singlesketch` computes it (reference call site pyani_plus/methods/sourmash.py:67-83;
+// conventions SURVEY.md 8c; Appendix B for the 31-byte specialisation).
+//
+// The code is __host__ __device__ so that tests can run the identical logic on the CPU
+// (csrc/hostemu.cpp) and compare it with the oracle before any GPU time is spent.
+//
+// Thread geometry ("stride-4" scheme).  A tile is 4096 k-mer start positions handled by 256 threads.
+// Thread (u = tid>>2, a = tid&3) owns the 16 k-mers starting at tile positions 64u + a + 4j,
+// j = 0..15.  Because the starts are 4 bases = 4 ASCII bytes apart, the ASCII form of the thread's
+// SPAN = 60+K bases, expanded ONCE into NA 32-bit registers, contains every one of the 16 k-mers as
+// a register-aligned window G[j .. j+NWD): no per-k-mer byte shifting is needed.  The same holds for
+// the reverse strand: the reverse complement of the whole span, expanded once into H[], contains the
+// reverse complement of k-mer j as H[15-j .. 15-j+NWD) (SPAN-K = 60 is a multiple of 4).
+// The canonical choice is made on the packed 2-bit form: with bases packed LSB-first (base i at
+// bits 2i), fwd < revcomp lexicographically  <=>  F_lsb < R_lsb as integers, where F_lsb / R_lsb are
+// the 2K-bit windows of the packed span and of its packed reverse complement (the MSB-first code
+// of one strand is the bitwise complement of the LSB-first code of the other).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PANIB_HD __host__ __device__ __forceinline__
+#else
+#define PANIB_HD inline
+#endif
+
+namespace panib {
+
+constexpr int kTileBases = 4096;     // == PANIB_TILE_BASES
+constexpr int kThreadsK1 = 256;
+constexpr int kKmersPerThread = 16;  // 256 threads * 16 = 4096
+constexpr int kTileWords = kTileBases / 16 + 8;   // packed words staged per tile (tile + halo)
+constexpr int kTileMaskWords = kTileBases / 32 + 4;
+
+// ---- small intrinsics with host emulation ---------------------------------------------------
+PANIB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, s);
+#else
+    uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t sel = (s >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(pool >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+// funnel shift right: low 32 bits of ((hi:lo) >> s), 0 <= s <= 31
+PANIB_HD uint32_t shf_r(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+PANIB_HD uint32_t brev32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+#endif
+}
+PANIB_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+PANIB_HD uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+// ---- MurmurHash3_x64_128 h1 of a K-byte key held as little-endian 32-bit words W[0..ceil(K/4)) ----
+// Bytes of W beyond K are ignored (masked here), so W may be a window of a longer byte string.
+template <int K>
+PANIB_HD uint64_t murmur_words(const uint32_t *W, uint32_t seed) {
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    constexpr int nblocks = K / 16;
+#pragma unroll
+    for (int i = 0; i < nblocks; i++) {
+        uint64_t k1 = ((uint64_t)W[4 * i + 1] << 32) | W[4 * i];
+        uint64_t k2 = ((uint64_t)W[4 * i + 3] << 32) | W[4 * i + 2];
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    constexpr int tail = K & 15;
+    constexpr int tb = 4 * nblocks;  // first tail word
+    if (tail > 8) {
+        constexpr int nb2 = tail - 8;  // 1..7 bytes in k2
+        uint32_t lo = W[tb + 2];
+        uint32_t hi = nb2 > 4 ? W[tb + 3] : 0u;
+        if (nb2 < 4) lo &= (1u << (8 * (nb2 & 3))) - 1u;
+        if (nb2 > 4 && nb2 < 8) hi &= (1u << (8 * (nb2 & 3))) - 1u;
+        uint64_t k2 = ((uint64_t)hi << 32) | lo;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    }
+    if (tail > 0) {
+        constexpr int nb1 = tail > 8 ? 8 : tail;  // 1..8 bytes in k1
+        uint32_t lo = W[tb];
+        uint32_t hi = nb1 > 4 ? W[tb + 1] : 0u;
+        if (nb1 < 4) lo &= (1u << (8 * (nb1 & 3))) - 1u;
+        if (nb1 > 4 && nb1 < 8) hi &= (1u << (8 * (nb1 & 3))) - 1u;
+        uint64_t k1 = ((uint64_t)hi << 32) | lo;
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+
+// ---- geometry of one thread's span for k-mer size K ------------------------------------------
+template <int K>
+struct Geom {
+    static_assert(K >= 1 && K <= 32, "register-resident kernel handles 1 <= K <= 32");
+    static constexpr int SPAN = 4 * (kKmersPerThread - 1) + K;  // bases touched by one thread
+    static constexpr int NX = (2 * SPAN + 6 + 31) / 32;         // packed words (incl. 0..6 bits of alignment)
+    static constexpr int NA = (SPAN + 3) / 4;                   // ASCII words per strand
+    static constexpr int NWD = (K + 3) / 4;                     // ASCII words per k-mer
+    static constexpr int RCSHIFT = 2 * (16 * NX - SPAN);        // bits to drop after pair-reversal
+};
+
+// 16 bases (one packed word) -> 4 ASCII words.  LUT byte c = ASCII of code c.
+PANIB_HD void expand16(uint32_t x, uint32_t *out4) {
+    const uint32_t lut = 0x54474341u;  // 'A','C','G','T' for codes 0..3
+    // spread each byte (4 bases) to 4 nibbles: PRMT puts bytes b0,b1 (b2,b3) into even byte lanes,
+    // two shift-or-mask steps finish the 2-bit -> 4-bit spread; the nibbles are PRMT selectors.
+    uint32_t lo = prmt(x, 0u, 0x4140u);  // [b0, 0, b1, 0]
+    uint32_t hi = prmt(x, 0u, 0x4342u);  // [b2, 0, b3, 0]
+    lo = (lo | (lo << 4)) & 0x0F0F0F0Fu;
+    hi = (hi | (hi << 4)) & 0x0F0F0F0Fu;
+    lo = (lo | (lo << 2)) & 0x33333333u;
+    hi = (hi | (hi << 2)) & 0x33333333u;
+    out4[0] = prmt(lut, 0u, lo);
+    out4[1] = prmt(lut, 0u, lo >> 16);
+    out4[2] = prmt(lut, 0u, hi);
+    out4[3] = prmt(lut, 0u, hi >> 16);
+}
+
+// reverse the order of the 16 2-bit fields of a word and complement them
+PANIB_HD uint32_t revcomp16(uint32_t x) {
+    uint32_t r = brev32(x);
+    return ~(((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1));
+}
+
+// 2K-bit window of a packed multiword value starting at (compile-time) bit offset `off`, as u64.
+template <int K, int NXW>
+PANIB_HD uint64_t window(const uint32_t *X, int off) {
+    const int w = off >> 5, s = off & 31;
+    uint32_t lo, hi;
+    if (s == 0) {
+        lo = X[w];
+        hi = (2 * K > 32) ? X[w + 1] : 0u;
+    } else {
+        lo = shf_r(X[w], (w + 1 < NXW) ? X[w + 1] : 0u, s);
+        hi = (2 * K > 32) ? shf_r((w + 1 < NXW) ? X[w + 1] : 0u, (w + 2 < NXW) ? X[w + 2] : 0u, s) : 0u;
+    }
+    if (2 * K < 32) lo &= (1u << ((2 * K) & 31)) - 1u;
+    if (2 * K > 32 && 2 * K < 64) hi &= (1u << ((2 * K) & 31)) - 1u;
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// Hash the 16 k-mers of thread (u, a) of a tile.
+//   sp   : packed words of the tile (word 0 bit 0 = tile position 0), kTileWords valid words
+//   sm   : validity-mask words of the tile (bit set = invalid), kTileMaskWords valid words
+//   emit : callable(uint64_t h) invoked for every VALID k-mer (caller applies the max_hash test)
+// DIRTY=false skips the per-k-mer validity test (caller guarantees the tile has no invalid base).
+template <int K, bool DIRTY, class Emit>
+PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, int a, uint32_t seed,
+                                Emit &&emit) {
+    using G_ = Geom<K>;
+    constexpr int NX = G_::NX, NA = G_::NA, NWD = G_::NWD;
+    const uint32_t *src = sp + 4 * u;  // span starts at tile position 64u + a
+    uint32_t X[NX];
+#pragma unroll
+    for (int w = 0; w < NX - 1; w++) X[w] = shf_r(src[w], src[w + 1], 2 * a);
+    X[NX - 1] = src[NX - 1] >> (2 * a);
+
+    // packed reverse complement of the span, LSB-first: Xr base p = comp(X base SPAN-1-p)
+    uint32_t Z[NX + 2];
+#pragma unroll
+    for (int w = 0; w < NX; w++) Z[w] = revcomp16(X[NX - 1 - w]);
+    Z[NX] = 0u;
+    Z[NX + 1] = 0u;
+    uint32_t Xr[NX];
+    constexpr int wo = G_::RCSHIFT >> 5, sh = G_::RCSHIFT & 31;
+#pragma unroll
+    for (int w = 0; w < NX; w++) {
+        uint32_t l = (w + wo < NX) ? Z[w + wo] : 0u;
+        uint32_t h = (w + wo + 1 < NX) ? Z[w + wo + 1] : 0u;
+        Xr[w] = sh ? shf_r(l, h, sh) : l;
+    }
+
+    // ASCII expansion of both strands (each base expanded once per thread)
+    uint32_t G[4 * NX], H[4 * NX];
+#pragma unroll
+    for (int w = 0; w < NX; w++) {
+        if (4 * w < NA) {
+            expand16(X[w], &G[4 * w]);
+            expand16(Xr[w], &H[4 * w]);
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < kKmersPerThread; j++) {
+        bool valid = true;
+        if (DIRTY) {
+            const int pos = 64 * u + a + 4 * j;
+            uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
+            if (K < 32) mw &= (1u << (K & 31)) - 1u;
+            valid = (mw == 0u);
+        }
+        const uint64_t F = window<K, NX>(X, 8 * j);
+        const uint64_t R = window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
+        const bool fwd = F < R;
+        uint32_t W[NWD];
+#pragma unroll
+        for (int i = 0; i < NWD; i++) W[i] = fwd ? G[j + i] : H[kKmersPerThread - 1 - j + i];
+        const uint64_t h = murmur_words<K>(W, seed);
+        if (!DIRTY || valid) emit(h);
+    }
+}
+
+}  // namespace panib

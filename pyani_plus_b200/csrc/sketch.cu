@@ -1,0 +1,341 @@
+// sketch.cu -- stage 0 (pack) and stage 1 (kernel K1: FracMinHash sketching) of libpanib200.so.
+//
+// Replaces the arithmetic of `sourmash scripts singlesketch -I DNA -p k=K,scaled=S`
+// (reference call site: pyani_plus/methods/sourmash.py:67-83, prepare_genomes :34-84).
+//
+// K1 is integer-ALU bound by construction (about 12 64-bit multiplies + rotates per k-mer, see
+// DESIGN.md), so the design goal is instructions per k-mer, not bytes: the 2-bit stream is staged
+// once per tile in shared memory (tile + K-1 halo), every base is expanded to ASCII once per thread
+// (kmer_hash.cuh), and the only global writes are the ~1/scaled surviving hashes, inserted into
+// value-range buckets of the genome's row so that a per-bucket sort yields the globally sorted,
+// duplicate-free sketch.
+#include "common.cuh"
+#include "kmer_hash.cuh"
+#include "pack.cuh"
+
+namespace panib {
+
+// ------------------------------------------------------------------------------------------------
+// stage 0: ASCII stream -> 2-bit packed + validity mask.  One thread per 32 bases (two 16-byte loads).
+// HBM-bound: 1 B/base read, 0.375 B/base written.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_ascii_kernel(const uint4 *__restrict__ ascii, int64_t n_groups,
+                                                         uint32_t *__restrict__ packed,
+                                                         uint32_t *__restrict__ mask) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const uint4 a = __ldg(&ascii[2 * g]);
+        const uint4 b = __ldg(&ascii[2 * g + 1]);
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+        uint32_t ia, ib;
+        const uint32_t pa = pack16(wa, ia);
+        const uint32_t pb = pack16(wb, ib);
+        reinterpret_cast<uint2 *>(packed)[g] = make_uint2(pa, pb);
+        mask[g] = ia | (ib << 16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// insertion of a surviving hash into its genome's bucketed table
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void table_insert(uint64_t *__restrict__ row, int nb, uint64_t bmul, uint64_t h,
+                                             int32_t *flag, int32_t *status) {
+    if (h == kEmpty) {  // only reachable when max_hash == 2^64-1 (scaled == 1); kept as a flag
+        atomicOr(flag, 1);
+        return;
+    }
+    uint32_t b = 0;
+    if (nb > 1) {
+        b = (uint32_t)__umul64hi(h, bmul);
+        if (b >= (uint32_t)nb) b = (uint32_t)nb - 1u;
+    }
+    unsigned long long *bucket = reinterpret_cast<unsigned long long *>(row) + (size_t)b * kBucketSlots;
+    uint32_t s = (uint32_t)h & (kBucketSlots - 1);
+    for (int probe = 0; probe < kBucketSlots; ++probe) {
+        const unsigned long long prev = atomicCAS(&bucket[s], (unsigned long long)kEmpty, (unsigned long long)h);
+        if (prev == kEmpty || prev == h) return;  // inserted, or already present (set semantics)
+        s = (s + 1) & (kBucketSlots - 1);
+    }
+    atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);
+}
+
+struct EmitToTable {
+    uint64_t *row;
+    int nb;
+    uint64_t bmul;
+    uint64_t max_hash;
+    int32_t *flag;
+    int32_t *status;
+    __device__ __forceinline__ void operator()(uint64_t h) const {
+        // keep iff 0 < h <= max_hash (sourmash skips hash 0)
+        if (h - 1ull < max_hash) table_insert(row, nb, bmul, h, flag, status);
+    }
+};
+
+// stage the tile (+halo) of the packed stream and of the mask into shared memory; find the genome.
+// Returns true when the tile holds at least one invalid base.
+template <int NWORDS, int NMASK>
+__device__ __forceinline__ bool stage_tile(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                                           const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile,
+                                           uint32_t *sp, uint32_t *sm, int *s_genome) {
+    const int tid = threadIdx.x;
+    const uint32_t *gp = packed + tile * (kTileBases / 16);
+    const uint32_t *gm = mask + tile * (kTileBases / 32);
+    for (int i = tid; i < NWORDS; i += blockDim.x) sp[i] = __ldg(gp + i);
+    uint32_t any = 0;
+    for (int i = tid; i < NMASK; i += blockDim.x) {
+        const uint32_t m = __ldg(gm + i);
+        sm[i] = m;
+        any |= m;
+    }
+    if (tid == 0) {  // largest g with tile_off[g] <= tile
+        int lo = 0, hi = n_genomes - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(tile_off + mid) <= tile) lo = mid; else hi = mid - 1;
+        }
+        *s_genome = lo;
+    }
+    return __syncthreads_or(any != 0u) != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, register-resident form for compile-time K <= 32 (see kmer_hash.cuh for the thread geometry)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kThreadsK1, 2)
+sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                   const int64_t *__restrict__ tile_off, int n_genomes, uint32_t seed, uint64_t max_hash,
+                   const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
+                   uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
+    __shared__ __align__(16) uint32_t sp[kTileWords];
+    __shared__ __align__(16) uint32_t sm[kTileMaskWords];
+    __shared__ int s_genome;
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+    const bool dirty = stage_tile<kTileWords, kTileMaskWords>(packed, mask, tile_off, n_genomes, tile, sp, sm,
+                                                              &s_genome);
+    const int g = s_genome;
+    EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g, status};
+    const int u = threadIdx.x >> 2, a = threadIdx.x & 3;
+    if (!dirty) {
+        hash_thread_kmers<K, false>(sp, sm, u, a, seed, emit);
+    } else {
+        hash_thread_kmers<K, true>(sp, sm, u, a, seed, emit);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, generic form for any 1 <= k <= 255 (run-time k): one k-mer per thread-iteration, bases read
+// from the staged 2-bit tile.  Correctness path for unusual k; not tuned.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGenWords = (kTileBases + 256) / 16 + 1;
+constexpr int kGenMask = (kTileBases + 256) / 32 + 1;
+
+__device__ __forceinline__ uint32_t base_at(const uint32_t *sp, int pos) {
+    return (sp[pos >> 4] >> (2 * (pos & 15))) & 3u;
+}
+
+__global__ void __launch_bounds__(256)
+sketch_hash_generic_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                           const int64_t *__restrict__ tile_off, int n_genomes, int k, uint32_t seed,
+                           uint64_t max_hash, const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
+                           uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
+    __shared__ uint32_t sp[kGenWords];
+    __shared__ uint32_t sm[kGenMask];
+    __shared__ int s_genome;
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+    stage_tile<kGenWords, kGenMask>(packed, mask, tile_off, n_genomes, tile, sp, sm, &s_genome);
+    const int g = s_genome;
+    EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g, status};
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    const uint32_t lut = 0x54474341u;
+    for (int pos = threadIdx.x; pos < kTileBases; pos += blockDim.x) {
+        bool valid = true;
+        for (int i = 0; i < k; i++) valid &= ((sm[(pos + i) >> 5] >> ((pos + i) & 31)) & 1u) == 0u;
+        if (!valid) continue;
+        bool fwd = true;  // lexicographic compare of the k-mer with its reverse complement
+        for (int i = 0; i < k; i++) {
+            const uint32_t f = base_at(sp, pos + i), r = 3u - base_at(sp, pos + k - 1 - i);
+            if (f != r) { fwd = f < r; break; }
+        }
+        auto key_byte = [&](int i) -> uint64_t {
+            const uint32_t c = fwd ? base_at(sp, pos + i) : 3u - base_at(sp, pos + k - 1 - i);
+            return (lut >> (8 * c)) & 0xFFu;
+        };
+        uint64_t h1 = seed, h2 = seed;
+        const int nblocks = k / 16;
+        for (int b = 0; b < nblocks; b++) {
+            uint64_t k1 = 0, k2 = 0;
+            for (int t = 0; t < 8; t++) {
+                k1 |= key_byte(16 * b + t) << (8 * t);
+                k2 |= key_byte(16 * b + 8 + t) << (8 * t);
+            }
+            k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+            h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+            k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+            h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        }
+        const int tail = k & 15, tb = 16 * nblocks;
+        if (tail > 8) {
+            uint64_t k2 = 0;
+            for (int t = 8; t < tail; t++) k2 |= key_byte(tb + t) << (8 * (t - 8));
+            k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        }
+        if (tail > 0) {
+            uint64_t k1 = 0;
+            for (int t = 0; t < (tail < 8 ? tail : 8); t++) k1 |= key_byte(tb + t) << (8 * t);
+            k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        }
+        h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
+        h1 += h2; h2 += h1;
+        h1 = fmix64(h1); h2 = fmix64(h2);
+        h1 += h2;
+        emit(h1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: per genome, sort every bucket, drop the empty slots and compact the row in place.
+// One CTA per genome; a bucket (1024 slots, 8 KB) is bitonic-sorted in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sketch_finalize_kernel(uint64_t *__restrict__ table, int64_t row_stride, const int32_t *__restrict__ nb,
+                       int32_t *__restrict__ counts, const int32_t *__restrict__ flags) {
+    __shared__ uint64_t s[kBucketSlots];
+    __shared__ int s_cnt;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    uint64_t *row = table + (size_t)g * row_stride;
+    const int n = nb[g];
+    int off = 0;
+    for (int b = 0; b < n; b++) {
+        for (int i = tid; i < kBucketSlots; i += 256) s[i] = row[(size_t)b * kBucketSlots + i];
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int k = 2; k <= kBucketSlots; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < kBucketSlots / 2; t += 256) {
+                    const int i = 2 * t - (t & (j - 1));  // index with bit j clear
+                    const int p = i | j;
+                    const bool up = (i & k) == 0;
+                    const uint64_t x = s[i], y = s[p];
+                    if ((x > y) == up) { s[i] = y; s[p] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < kBucketSlots; i += 256) {
+            if (s[i] != kEmpty && (i == kBucketSlots - 1 || s[i + 1] == kEmpty)) s_cnt = i + 1;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int i = tid; i < cnt; i += 256) row[off + i] = s[i];
+        off += cnt;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if ((flags[g] & 1) && off < row_stride) row[off++] = kEmpty;  // the all-ones hash (scaled == 1 only)
+        counts[g] = off;
+    }
+}
+
+}  // namespace panib
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace panib;
+
+static dim3 tile_grid(int64_t n_tiles) {
+    const int64_t gx = n_tiles < 65536 * 16 ? n_tiles : 65536 * 16;
+    const int64_t gy = (n_tiles + gx - 1) / gx;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+extern "C" int panib_pack_ascii(const uint8_t *d_ascii, int64_t n_bases, uint32_t *d_packed, uint32_t *d_mask,
+                                void *stream) {
+    if (n_bases < 0 || (n_bases & 31)) {
+        set_error("panib_pack_ascii: n_bases=%lld must be a non-negative multiple of 32", (long long)n_bases);
+        return PANIB_E_ARG;
+    }
+    if (n_bases == 0) return PANIB_OK;
+    const int64_t groups = n_bases / 32;
+    const int64_t want = (groups + 255) / 256;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+    pack_ascii_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4 *>(d_ascii), groups,
+                                                                 d_packed, d_mask);
+    return check_launch("pack_ascii_kernel");
+}
+
+extern "C" int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
+                                      int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                                      const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                                      int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream) {
+    if (k < 1 || k > PANIB_MAX_K) {
+        set_error("k-mer size %d outside 1..%d", k, PANIB_MAX_K);
+        return PANIB_E_ARG;
+    }
+    if (n_genomes <= 0 || n_tiles <= 0) return PANIB_OK;
+    if (row_stride <= 0 || row_stride % kBucketSlots) {
+        set_error("row_stride=%lld must be a positive multiple of %d", (long long)row_stride, kBucketSlots);
+        return PANIB_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PANIB_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
+    PANIB_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
+    const dim3 grid = tile_grid(n_tiles);
+    if ((int64_t)grid.x * grid.y != n_tiles) {
+        set_error("n_tiles=%lld cannot be tiled into a grid", (long long)n_tiles);
+        return PANIB_E_ARG;
+    }
+#define PANIB_LAUNCH_K(KK)                                                                                    \
+    sketch_hash_kernel<KK><<<grid, kThreadsK1, 0, st>>>(d_packed, d_mask, d_tile_off, (int)n_genomes, seed,   \
+                                                         max_hash, d_nb, d_bmul, d_table, row_stride, d_flags, \
+                                                         d_status)
+    switch (k) {
+    case 21: PANIB_LAUNCH_K(21); break;
+    case 31: PANIB_LAUNCH_K(31); break;
+    default:
+        sketch_hash_generic_kernel<<<grid, 256, 0, st>>>(d_packed, d_mask, d_tile_off, (int)n_genomes, k, seed,
+                                                         max_hash, d_nb, d_bmul, d_table, row_stride, d_flags,
+                                                         d_status);
+    }
+#undef PANIB_LAUNCH_K
+    return check_launch("sketch_hash_kernel");
+}
+
+extern "C" int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int64_t n_genomes, const int32_t *d_nb,
+                                     int32_t *d_counts, const int32_t *d_flags, void *stream) {
+    if (n_genomes <= 0) return PANIB_OK;
+    sketch_finalize_kernel<<<(unsigned)n_genomes, 256, 0, (cudaStream_t)stream>>>(d_table, row_stride, d_nb,
+                                                                                   d_counts, d_flags);
+    return check_launch("sketch_finalize_kernel");
+}
+
+extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
+                                   int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                                   const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                                   int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
+                                   void *stream) {
+    int rc = panib_sketch_hash_only(d_packed, d_mask, d_tile_off, n_genomes, n_tiles, k, seed, max_hash, d_nb,
+                                    d_bmul, d_table, row_stride, d_flags, d_status, stream);
+    if (rc) return rc;
+    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, stream);
+}
+
+extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
+                                       uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
+                                       int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                                       const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                                       int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
+                                       void *stream) {
+    if (n_bases != (n_tiles + 1) * (int64_t)kTileBases) {
+        set_error("n_bases=%lld must equal (n_tiles+1)*%d", (long long)n_bases, kTileBases);
+        return PANIB_E_ARG;
+    }
+    PANIB_CUDA(cudaMemcpyAsync(d_ascii, h_ascii, (size_t)n_bases, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    int rc = panib_pack_ascii(d_ascii, n_bases, d_packed, d_mask, stream);
+    if (rc) return rc;
+    return panib_sketch_stream(d_packed, d_mask, d_tile_off, n_genomes, n_tiles, k, seed, max_hash, d_nb, d_bmul,
+                               d_table, row_stride, d_counts, d_flags, d_status, stream);
+}

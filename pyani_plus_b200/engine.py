@@ -1,0 +1,368 @@
+"""ctypes binding of ``libpanib200.so`` (C ABI: ``include/panib200.h``) plus device-buffer plumbing.
+
+PyTorch is used only to own device / pinned memory and the CUDA stream; every kernel is ours.
+There is deliberately NO CPU fallback: if the shared library is missing or no CUDA device is
+visible, constructing :class:`Engine` raises.
+
+What the engine replaces in the reference: the two external commands of
+``pyani_plus/methods/sourmash.py`` -- ``sourmash scripts singlesketch`` (:67-83) and
+``sourmash scripts manysearch`` (:184-200).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from pyani_plus_b200 import stream as _stream
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libpanib200.so"
+
+PROGRAM = "panib200"  # recorded as Configuration.program (the reference records "sourmash")
+
+ST_BUCKET_OVERFLOW = 1
+ST_SEGMENT_OVERFLOW = 2
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_u64 = ctypes.c_uint64
+_i32 = ctypes.c_int
+_u32 = ctypes.c_uint32
+
+
+class EngineError(RuntimeError):
+    """The CUDA engine is unavailable or a call into it failed."""
+
+
+_lib: ctypes.CDLL | None = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libpanib200.so and declare the prototypes of include/panib200.h."""
+    global _lib  # noqa: PLW0603
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.is_file():
+        msg = (
+            f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            " There is no CPU fallback for the sourmash path."
+        )
+        raise EngineError(msg)
+    L = ctypes.CDLL(str(LIB_PATH))
+    L.panib_version.restype = ctypes.c_char_p
+    L.panib_last_error.restype = _i32
+    L.panib_last_error.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    L.panib_device_count.restype = _i32
+    L.panib_launch_count.restype = _u64
+    L.panib_max_hash.restype = _u64
+    L.panib_max_hash.argtypes = [_u64]
+    L.panib_plan_buckets.restype = _i32
+    L.panib_plan_buckets.argtypes = [_i64, _u64, ctypes.c_double, ctypes.POINTER(ctypes.c_int32),
+                                     ctypes.POINTER(_u64)]
+    L.panib_pack_ascii.restype = _i32
+    L.panib_pack_ascii.argtypes = [_vp, _i64, _vp, _vp, _vp]
+    sk_args = [_vp, _vp, _vp, _i64, _i64, _i32, _u32, _u64, _vp, _vp, _vp, _i64]
+    L.panib_sketch_stream.restype = _i32
+    L.panib_sketch_stream.argtypes = [*sk_args, _vp, _vp, _vp, _vp]
+    L.panib_sketch_hash_only.restype = _i32
+    L.panib_sketch_hash_only.argtypes = [*sk_args, _vp, _vp, _vp]
+    L.panib_sketch_finalize.restype = _i32
+    L.panib_sketch_finalize.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp]
+    L.panib_sketch_ascii_host.restype = _i32
+    L.panib_sketch_ascii_host.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp, _vp]
+    L.panib_intersect.restype = _i32
+    L.panib_intersect.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i32, _u64, _i64, _i32, _i32,
+                                  _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp]
+    L.panib_intersect_fence_entries.restype = _i64
+    L.panib_intersect_fence_entries.argtypes = [_i64, _i64, _u64, _i64, _i32, _i32]
+    L.panib_ani_device.restype = _i32
+    L.panib_ani_device.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]
+    L.panib_ani_host.restype = _i32
+    L.panib_ani_host.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]
+    L.panib_synth_ascii.restype = _i32
+    L.panib_synth_ascii.argtypes = [_u64, _i64, _i64, _i64, _vp, _vp]
+    _lib = L
+    return L
+
+
+def library_version() -> str:
+    return load_library().panib_version().decode()
+
+
+def max_hash(scaled: int) -> int:
+    """sourmash's max_hash for a ``scaled`` value (host arithmetic inside the C ABI library)."""
+    return int(load_library().panib_max_hash(scaled))
+
+
+def plan_buckets(n_kmers: int, scaled: int, slack: float = 1.0) -> tuple[int, int]:
+    nb = ctypes.c_int32()
+    bmul = _u64()
+    _check(load_library().panib_plan_buckets(n_kmers, scaled, slack, ctypes.byref(nb), ctypes.byref(bmul)))
+    return int(nb.value), int(bmul.value)
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        buf = ctypes.create_string_buffer(512)
+        load_library().panib_last_error(buf, 512)
+        msg = f"libpanib200 error {rc}: {buf.value.decode(errors='replace')}"
+        raise EngineError(msg)
+
+
+def ani_host(ov: np.ndarray, q_counts: np.ndarray, s_counts: np.ndarray, k: int) -> tuple[np.ndarray, np.ndarray]:
+    """(identity, cov_query) float64 matrices from intersection counts, libm ``pow`` on the host.
+
+    NaN where branchwater would print no row.  pyani-plus mapping (private_cli.py:1875-1887):
+    identity = max_containment_ani, cov_query = query_containment_ani.
+    """
+    ov = np.ascontiguousarray(ov, dtype=np.uint32)
+    q_counts = np.ascontiguousarray(q_counts, dtype=np.int32)
+    s_counts = np.ascontiguousarray(s_counts, dtype=np.int32)
+    nq, ns = ov.shape
+    ident = np.empty((nq, ns), dtype=np.float64)
+    cov = np.empty((nq, ns), dtype=np.float64)
+    _check(load_library().panib_ani_host(ov.ctypes.data, ns, q_counts.ctypes.data, nq, s_counts.ctypes.data, ns,
+                                         k, ident.ctypes.data, cov.ctypes.data))
+    return ident, cov
+
+
+@dataclass
+class SketchTable:
+    """Device-resident sketches: row g holds counts[g] ascending distinct hashes."""
+
+    rows: "torch.Tensor"  # noqa: F821, UP037  int64 storage of uint64 hashes, shape [n, stride]
+    counts: "torch.Tensor"  # noqa: F821, UP037  int32 [n]
+    k: int
+    scaled: int
+
+    @property
+    def n(self) -> int:
+        return int(self.rows.shape[0])
+
+    @property
+    def stride(self) -> int:
+        return int(self.rows.shape[1])
+
+    def to_host(self) -> list[np.ndarray]:
+        counts = self.counts.cpu().numpy()
+        rows = self.rows.cpu().numpy().view(np.uint64)
+        return [rows[g, : counts[g]].copy() for g in range(self.n)]
+
+
+class Engine:
+    """One engine per process / per GPU (``torch.cuda.current_device()``)."""
+
+    def __init__(self, device: int | None = None) -> None:
+        import torch  # noqa: PLC0415
+
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available() or self.lib.panib_device_count() < 1:
+            msg = "No CUDA device visible: the sourmash path of pyani_plus_b200 has no CPU fallback."
+            raise EngineError(msg)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.max_batch_bytes = 1 << 31  # ASCII bytes staged per sketch batch
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return int(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.lib.panib_launch_count())
+
+    def _read_status(self) -> int:
+        st = int(self.status[0].item())  # synchronises the stream
+        if st:
+            self.status.zero_()
+        return st
+
+    # ------------------------------------------------------------------ stage 0+1: sketch
+    def sketch_ascii_stream(
+        self, h_ascii, tile_off: np.ndarray, k: int, scaled: int, *, seed: int = 42, slack: float = 1.0,
+        from_host: bool = True, keep_buffers: dict | None = None,
+    ) -> SketchTable:
+        """Sketch every genome of one tiled ASCII base stream (``stream.py`` layout).
+
+        ``h_ascii`` is a pinned uint8 torch tensor when ``from_host`` (copied H2D inside the C call),
+        else a device tensor.  Retries with more buckets if a bucket overflowed.
+        """
+        torch = self.torch
+        n_genomes = len(tile_off) - 1
+        n_tiles = int(tile_off[-1])
+        n_bases = (n_tiles + 1) * _stream.TILE
+        if h_ascii.numel() != n_bases:
+            msg = f"ASCII stream has {h_ascii.numel()} bytes, expected {n_bases}"
+            raise ValueError(msg)
+        mh = max_hash(scaled)
+        bufs = keep_buffers if keep_buffers is not None else {}
+        while True:
+            nb = np.empty(n_genomes, dtype=np.int32)
+            bmul = np.empty(n_genomes, dtype=np.uint64)
+            for g in range(n_genomes):
+                n_kmers = int(tile_off[g + 1] - tile_off[g]) * _stream.TILE
+                nb[g], bmul[g] = plan_buckets(n_kmers, scaled, slack)
+            row_stride = int(nb.max()) * 1024 if n_genomes else 1024
+            d_tile_off = torch.from_numpy(tile_off.astype(np.int64)).to(self.device)
+            d_nb = torch.from_numpy(nb).to(self.device)
+            d_bmul = torch.from_numpy(bmul.view(np.int64)).to(self.device)
+            d_packed = bufs.get("packed")
+            if d_packed is None or d_packed.numel() != n_bases // 16:
+                d_packed = torch.empty(n_bases // 16, dtype=torch.int32, device=self.device)
+                d_mask = torch.empty(n_bases // 32, dtype=torch.int32, device=self.device)
+                bufs["packed"], bufs["mask"] = d_packed, d_mask
+            d_mask = bufs["mask"]
+            table = torch.empty((max(n_genomes, 1), row_stride), dtype=torch.int64, device=self.device)
+            counts = torch.zeros(max(n_genomes, 1), dtype=torch.int32, device=self.device)
+            flags = torch.empty(max(n_genomes, 1), dtype=torch.int32, device=self.device)
+            sk = (d_packed.data_ptr(), d_mask.data_ptr(), d_tile_off.data_ptr(), n_genomes, n_tiles, k, seed, mh,
+                  d_nb.data_ptr(), d_bmul.data_ptr(), table.data_ptr(), row_stride, counts.data_ptr(),
+                  flags.data_ptr(), self.status.data_ptr(), self._stream())
+            if from_host:
+                d_ascii = bufs.get("ascii")
+                if d_ascii is None or d_ascii.numel() != n_bases:
+                    d_ascii = torch.empty(n_bases, dtype=torch.uint8, device=self.device)
+                    bufs["ascii"] = d_ascii
+                _check(self.lib.panib_sketch_ascii_host(h_ascii.data_ptr(), d_ascii.data_ptr(), n_bases, *sk))
+            else:
+                _check(self.lib.panib_pack_ascii(h_ascii.data_ptr(), n_bases, d_packed.data_ptr(),
+                                                 d_mask.data_ptr(), self._stream()))
+                _check(self.lib.panib_sketch_stream(*sk))
+            st = self._read_status()
+            if st & ST_BUCKET_OVERFLOW:
+                if slack > 64:
+                    msg = "sketch buckets keep overflowing (more than 64x the expected number of hashes)"
+                    raise EngineError(msg)
+                slack *= 2
+                continue
+            return SketchTable(table[:n_genomes], counts[:n_genomes], k, scaled)
+
+    def sketch_genomes(self, genomes: list[list[bytes]], k: int, scaled: int, *, seed: int = 42) -> SketchTable:
+        """Sketch genomes given as lists of record sequences (what a FASTA parser yields).
+
+        Genomes are staged in batches of at most ``max_batch_bytes`` of pinned host memory; the
+        per-batch tables are compacted into one table whose stride is the largest sketch size.
+        """
+        torch = self.torch
+        lengths = [_stream.genome_stream_length(g) for g in genomes]
+        batches: list[tuple[int, int]] = []
+        start, acc = 0, 0
+        for i, length in enumerate(lengths):
+            need = (length // _stream.TILE + 1) * _stream.TILE
+            if i > start and acc + need > self.max_batch_bytes:
+                batches.append((start, i))
+                start, acc = i, 0
+            acc += need
+        if genomes:
+            batches.append((start, len(genomes)))
+        parts: list[SketchTable] = []
+        bufs: dict = {}
+        for b0, b1 in batches:
+            tile_off = _stream.plan_tiles(lengths[b0:b1])
+            nbytes = _stream.stream_bytes(tile_off)
+            h_ascii = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            _stream.fill_ascii_stream(h_ascii.numpy(), tile_off, genomes[b0:b1])
+            parts.append(self.sketch_ascii_stream(h_ascii, tile_off, k, scaled, seed=seed, keep_buffers=bufs))
+        return self.concat_tables(parts, k, scaled)
+
+    def concat_tables(self, parts: list[SketchTable], k: int, scaled: int) -> SketchTable:
+        """One table with a tight stride (largest sketch, rounded up to 16 slots = 128 bytes)."""
+        torch = self.torch
+        if not parts:
+            return SketchTable(torch.empty((0, 16), dtype=torch.int64, device=self.device),
+                               torch.empty(0, dtype=torch.int32, device=self.device), k, scaled)
+        max_count = max(int(p.counts.max().item()) if p.n else 0 for p in parts)
+        stride = max(16, (max_count + 15) // 16 * 16)
+        n = sum(p.n for p in parts)
+        rows = torch.empty((n, stride), dtype=torch.int64, device=self.device)
+        at = 0
+        for p in parts:
+            w = min(stride, p.stride)
+            rows[at: at + p.n, :w] = p.rows[:, :w]
+            at += p.n
+        counts = torch.cat([p.counts for p in parts])
+        return SketchTable(rows, counts, k, scaled)
+
+    def table_from_host(self, sketches: list[np.ndarray], k: int, scaled: int) -> SketchTable:
+        """Upload sorted duplicate-free uint64 sketches (e.g. read back from ``.sig`` files)."""
+        torch = self.torch
+        n = len(sketches)
+        max_count = max((len(s) for s in sketches), default=0)
+        stride = max(16, (max_count + 15) // 16 * 16)
+        host = np.zeros((n, stride), dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.int32)
+        for g, s in enumerate(sketches):
+            host[g, : len(s)] = s
+            counts[g] = len(s)
+        return SketchTable(torch.from_numpy(host.view(np.int64)).to(self.device),
+                           torch.from_numpy(counts).to(self.device), k, scaled)
+
+    # ------------------------------------------------------------------ stage 2: intersect
+    def intersect(self, q: SketchTable, s: SketchTable | None = None, *, rank: int = 0, world: int = 1,
+                  n_cells: int = 0, seg_cap: int = 0, idx_buckets: int = 0, max_count: int | None = None):
+        """uint32 intersection sizes as an int32 torch tensor [nq, ns] (device).
+
+        ``s is None`` = all-vs-all within ``q`` (only q < s is computed, the result is mirrored and
+        the diagonal holds the sketch sizes).
+        """
+        torch = self.torch
+        symmetric = s is None
+        if symmetric:
+            s = q
+        if (q.k, q.scaled) != (s.k, s.scaled):
+            msg = "query and subject sketches use different k / scaled"
+            raise ValueError(msg)
+        nq, ns = q.n, s.n
+        ov = torch.empty((nq, ns), dtype=torch.int32, device=self.device)
+        if nq == 0 or ns == 0:
+            return ov
+        mh = max_hash(q.scaled)
+        if max_count is None:
+            max_count = int(torch.maximum(q.counts.max(), s.counts.max()).item())
+        cells = n_cells
+        while True:
+            nfence = int(self.lib.panib_intersect_fence_entries(nq, ns, mh, max_count, cells, seg_cap))
+            fence = torch.empty(max(nfence, 1), dtype=torch.int32, device=self.device)
+            _check(self.lib.panib_intersect(
+                q.rows.data_ptr(), q.counts.data_ptr(), q.stride, nq,
+                s.rows.data_ptr(), s.counts.data_ptr(), s.stride, ns,
+                1 if symmetric else 0, mh, max_count, cells, seg_cap, idx_buckets,
+                fence.data_ptr(), ov.data_ptr(), ns, rank, world, self.status.data_ptr(), self._stream()))
+            st = self._read_status()
+            if st & ST_SEGMENT_OVERFLOW:
+                cells = max(2, cells * 2) if cells else max(2, 2 * -(-max_count // 4096))
+                if cells > 1 << 16:
+                    msg = "pairwise segments keep overflowing"
+                    raise EngineError(msg)
+                continue
+            return ov
+
+    # ------------------------------------------------------------------ stage 3: ANI
+    def ani_device(self, ov, q: SketchTable, s: SketchTable | None = None):
+        """(identity, cov_query) float64 device tensors, NaN where there is no row (CUDA pow)."""
+        torch = self.torch
+        if s is None:
+            s = q
+        ident = torch.empty((q.n, s.n), dtype=torch.float64, device=self.device)
+        cov = torch.empty((q.n, s.n), dtype=torch.float64, device=self.device)
+        _check(self.lib.panib_ani_device(ov.data_ptr(), s.n, q.counts.data_ptr(), q.n, s.counts.data_ptr(), s.n,
+                                         q.k, ident.data_ptr(), cov.data_ptr(), self._stream()))
+        return ident, cov
+
+    # ------------------------------------------------------------------ synthetic input (bench / tests)
+    def synth_ascii_stream(self, seed: int, g0: int, n_genomes: int, length: int):
+        """Device ASCII stream of synthetic genomes + its tile offsets (SURVEY.md 8d generator)."""
+        torch = self.torch
+        tiles_per = length // _stream.TILE + 1
+        tile_off = np.arange(n_genomes + 1, dtype=np.int64) * tiles_per
+        n_bases = (int(tile_off[-1]) + 1) * _stream.TILE
+        d_ascii = torch.full((n_bases,), _stream.PAD, dtype=torch.uint8, device=self.device)
+        _check(self.lib.panib_synth_ascii(seed, g0, n_genomes, length, d_ascii.data_ptr(), self._stream()))
+        return d_ascii, tile_off

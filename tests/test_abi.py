@@ -1,0 +1,108 @@
+"""The C-ABI library builds, loads and exports every symbol declared in include/panib200.h.
+
+No device compute here (CPU container): only the pure-host helpers are called.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from oracle import oracle
+
+HEADER = entry.ROOT / "include" / "panib200.h"
+
+
+@pytest.fixture(scope="module")
+def lib() -> ctypes.CDLL:
+    entry.build()
+    from pyani_plus_b200 import engine
+
+    return engine.load_library()
+
+
+def declared_symbols() -> list[str]:
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(panib_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib: ctypes.CDLL) -> None:
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in panib200.h but not exported"
+
+
+def test_header_cites_reference() -> None:
+    text = HEADER.read_text()
+    assert "pyani_plus/methods/sourmash.py:67-83" in text
+    assert "pyani_plus/methods/sourmash.py:184-200" in text
+
+
+def test_max_hash_matches_oracle_and_fixtures(lib: ctypes.CDLL) -> None:
+    from pyani_plus_b200 import engine
+
+    assert engine.max_hash(300) == 61489146912365176
+    assert engine.max_hash(1000) == 18446744073709552
+    for scaled in (1, 2, 3, 50, 100, 299, 300, 1000, 12345, 10**9, 2**40 + 1):
+        assert engine.max_hash(scaled) == oracle.max_hash(scaled) == oracle.py_max_hash(scaled)
+
+
+def test_plan_buckets_is_monotone_and_in_range(lib: ctypes.CDLL) -> None:
+    from pyani_plus_b200 import engine
+
+    for n_kmers, scaled in ((5_000_000, 1000), (5_000_000, 100), (40_000, 300), (18_000, 1), (100, 10**12)):
+        nb, bmul = engine.plan_buckets(n_kmers, scaled)
+        assert nb >= 1
+        mh = engine.max_hash(scaled)
+        for h in (1, mh // 3, mh // 2, mh - 1, mh):
+            assert (h * bmul) >> 64 < nb
+        assert (mh * bmul) >> 64 >= nb - 2  # the top bucket is used
+    with pytest.raises(Exception, match="bad arguments"):
+        engine.plan_buckets(-1, 1000)
+
+
+def test_ani_host_matches_oracle_exactly(lib: ctypes.CDLL) -> None:
+    from pyani_plus_b200 import engine
+
+    rng = np.random.default_rng(1)
+    qc = rng.integers(0, 6000, 40).astype(np.int32)
+    sc = rng.integers(0, 6000, 30).astype(np.int32)
+    ov = np.minimum(rng.integers(0, 6000, (40, 30)), np.minimum.outer(qc, sc)).astype(np.uint32)
+    ov[3, :] = 0
+    for k in (31, 21):
+        ident, cov = engine.ani_host(ov, qc, sc, k)
+        for i in range(40):
+            for j in range(30):
+                row = oracle.pair_row(int(ov[i, j]), int(qc[i]), int(sc[j]), k)
+                if row is None:
+                    assert np.isnan(ident[i, j]) and np.isnan(cov[i, j])
+                else:
+                    assert ident[i, j] == row["max_containment_ani"]
+                    assert cov[i, j] == row["query_containment_ani"]
+
+
+def test_engine_fails_loudly_without_gpu() -> None:
+    """No CPU fallback: constructing the engine on a box without CUDA must raise."""
+    import torch
+
+    from pyani_plus_b200 import engine
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(engine.EngineError, match="no CPU fallback"):
+        engine.Engine()
+
+
+def test_product_never_imports_oracle() -> None:
+    """The oracle is test infrastructure; nothing under pyani_plus_b200/ may reference it."""
+    for path in Path(entry.PKG).rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".cpp", ".h"}:
+            text = path.read_text()
+            assert "import oracle" not in text and "from oracle" not in text, path
+            assert "liboracle" not in text, path

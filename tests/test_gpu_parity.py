@@ -1,0 +1,247 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden fixtures.
+
+Bars (BASELINE.json north_star): hashes and intersection counts bit-exact; ANI within 1e-12 absolute
+(the host-finalised ANI used by the drop-in path must in fact be exactly equal).
+"""
+
+from __future__ import annotations
+
+import csv
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261017
+ANI_ATOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pyani_plus_b200 import engine
+
+    return engine.Engine(0)
+
+
+def _records(path: Path) -> list[bytes]:
+    return [s for _, s in oracle.fasta_records(oracle.read_bytes_maybe_gz(path))]
+
+
+def _fasta_files(d: Path) -> list[Path]:
+    return sorted(p for p in d.iterdir() if p.is_file() and ".f" in p.name)
+
+
+@pytest.mark.parametrize(("name", "scaled"), [("viral_example", 300), ("bad_alignments", 300),
+                                              ("bacterial_example", 1000)])
+def test_fixture_sigs_and_manysearch(eng, golden: Path, name: str, scaled: int) -> None:
+    """GPU sketches == fixture .sig mins; GPU counts + host ANI == manysearch.csv values exactly."""
+    from pyani_plus_b200 import engine
+
+    files = _fasta_files(golden / name)
+    md5s = [oracle.file_md5(f) for f in files]
+    table = eng.sketch_genomes([_records(f) for f in files], 31, scaled)
+    got = dict(zip(md5s, table.to_host(), strict=True))
+    for md5, hashes in got.items():
+        (outer,) = json.loads((golden / name / "intermediates" / "sourmash" / f"{md5}.sig").read_text())
+        (sig,) = outer["signatures"]
+        assert hashes.tolist() == sig["mins"]
+        assert sig["max_hash"] == engine.max_hash(scaled)
+        assert oracle.sig_md5sum(hashes) == sig["md5sum"]
+    ov = eng.intersect(table).cpu().numpy()
+    counts = table.counts.cpu().numpy()
+    ident, cov = engine.ani_host(ov.astype(np.uint32), counts, counts, 31)
+    ident_d, cov_d = (t.cpu().numpy() for t in eng.ani_device(eng.intersect(table), table))
+    rows = list(csv.DictReader((golden / name / "intermediates" / "sourmash" / "manysearch.csv").open()))
+    seen = set()
+    for row in rows:
+        i, j = md5s.index(row["query_name"]), md5s.index(row["match_name"])
+        seen.add((i, j))
+        assert ov[i, j] == int(row["intersect_hashes"])
+        assert ident[i, j] == float(row["max_containment_ani"])  # exact
+        assert cov[i, j] == float(row["query_containment_ani"])  # exact
+        assert abs(ident_d[i, j] - float(row["max_containment_ani"])) <= ANI_ATOL
+        assert abs(cov_d[i, j] - float(row["query_containment_ani"])) <= ANI_ATOL
+    for i in range(len(md5s)):
+        for j in range(len(md5s)):
+            if (i, j) not in seen:  # no manysearch row <=> NULL
+                assert ov[i, j] == 0
+                assert np.isnan(ident[i, j]) and np.isnan(cov[i, j])
+                assert np.isnan(ident_d[i, j]) and np.isnan(cov_d[i, j])
+
+
+def test_coverage_scaled50_with_n_run(eng, golden: Path) -> None:
+    """Reference tests/test_coverage.py:162-174 (28-N run, two-record genome, nulls)."""
+    from pyani_plus_b200 import engine
+
+    exp = json.loads((golden / "expected.json").read_text())["test_coverage_scaled50"]
+    small = _records(golden / "MIBY01000005.fasta")
+    large = _records(golden / "MIBY01000011.fasta")
+    # sorted-md5 order of the reference test: small, both, large
+    table = eng.sketch_genomes([small, small + large, large], 31, 50)
+    counts = table.counts.cpu().numpy()
+    assert counts.tolist() == [148, 488, 340]
+    ov = eng.intersect(table).cpu().numpy()
+    ident, cov = engine.ani_host(ov.astype(np.uint32), counts, counts, 31)
+    for i in range(3):
+        for j in range(3):
+            want_id, want_cov = exp["df_identity_data"][i][j], exp["df_cov_query_data"][i][j]
+            if want_id is None:
+                assert np.isnan(ident[i, j])
+            else:
+                assert round(float(ident[i, j]), 10) == want_id
+                assert round(float(cov[i, j]), 10) == want_cov
+
+
+@pytest.mark.parametrize("k", [31, 21, 7, 15, 16, 32, 33, 51])
+def test_kmer_sizes_vs_oracle(eng, golden: Path, k: int) -> None:
+    """Fast kernels (k=21,31) and the generic kernel (every other k) vs the oracle; includes N runs,
+    lower case and a multi-record genome."""
+    genomes = [
+        _records(golden / "MIBY01000005.fasta"),
+        [r.lower() for r in _records(golden / "MIBY01000011.fasta")],
+        _records(golden / "MIBY01000005.fasta") + _records(golden / "MIBY01000011.fasta"),
+        _records(golden / "viral_example" / "OP073605.fasta"),
+        [b"ACGT" * 3],  # shorter than most k
+        [],
+        [b"ACGTNNACGTTTGACCA" * 40, b"", b"TTGACCAGTA" * 50],
+    ]
+    scaled = 20
+    got = eng.sketch_genomes(genomes, k, scaled).to_host()
+    for g, recs in enumerate(genomes):
+        want = oracle.sketch_records(recs, k, scaled)
+        assert got[g].tolist() == want.tolist(), (k, g)
+
+
+def test_scaled_one_keeps_everything(eng, golden: Path) -> None:
+    recs = _records(golden / "MIBY01000011.fasta")
+    got = eng.sketch_genomes([recs], 31, 1).to_host()[0]
+    want = oracle.sketch_records(recs, 31, 1)
+    assert got.tolist() == want.tolist()
+    assert len(got) > 17000
+
+
+def test_exact_tile_multiple_and_boundaries(eng) -> None:
+    """Genome lengths around the 4096-base tile size; k-mers must not leak across genomes."""
+    base = oracle.synth_genome(SEED, 3, 3 * 4096 + 64)
+    genomes = [[base[:n]] for n in (4095, 4096, 4097, 8192, 8192 + 30, 8192 + 31, 30, 31, 32, 12288)]
+    got = eng.sketch_genomes(genomes, 31, 10).to_host()
+    for g, recs in enumerate(genomes):
+        assert got[g].tolist() == oracle.sketch_records(recs, 31, 10).tolist(), g
+
+
+def test_synthetic_family_counts_and_ani(eng) -> None:
+    """BASELINE config-2 shaped (scaled down): sketches, full count matrix and ANI vs the oracle."""
+    from pyani_plus_b200 import engine
+
+    n, length, k, scaled = 24, 200_000, 31, 100
+    genomes = [[oracle.synth_genome(SEED, g, length)] for g in range(n)]
+    table = eng.sketch_genomes(genomes, k, scaled)
+    want_hashes, want_counts = oracle.synth_sketch_batch(SEED, 0, n, length, k, scaled)
+    got = table.to_host()
+    for g in range(n):
+        assert got[g].tolist() == want_hashes[g, : want_counts[g]].tolist()
+    want_ov = oracle.intersect_all(want_hashes, want_counts)
+    ov = eng.intersect(table).cpu().numpy()
+    assert (ov.astype(np.int64) == want_ov).all()
+    counts = table.counts.cpu().numpy()
+    ident, cov = engine.ani_host(ov.astype(np.uint32), counts, counts, k)
+    ident_d, cov_d = (t.cpu().numpy() for t in eng.ani_device(eng.intersect(table), table))
+    for i in range(n):
+        for j in range(n):
+            row = oracle.pair_row(int(want_ov[i, j]), int(want_counts[i]), int(want_counts[j]), k)
+            if row is None:
+                assert np.isnan(ident[i, j]) and np.isnan(ident_d[i, j])
+            else:
+                assert ident[i, j] == row["max_containment_ani"]
+                assert cov[i, j] == row["query_containment_ani"]
+                assert abs(ident_d[i, j] - row["max_containment_ani"]) <= ANI_ATOL
+                assert abs(cov_d[i, j] - row["query_containment_ani"]) <= ANI_ATOL
+
+
+def test_device_generator_matches_oracle(eng) -> None:
+    from pyani_plus_b200 import stream
+
+    n, length = 5, 10_000
+    d_ascii, tile_off = eng.synth_ascii_stream(SEED, 7, n, length)
+    host = d_ascii.cpu().numpy()
+    for g in range(n):
+        at = int(tile_off[g]) * stream.TILE
+        assert host[at: at + length].tobytes() == oracle.synth_genome(SEED, 7 + g, length)
+        assert (host[at + length: int(tile_off[g + 1]) * stream.TILE] == ord("N")).all()
+
+
+@pytest.mark.parametrize(("cells", "seg_cap"), [(0, 0), (1, 6144), (3, 6144), (7, 2048), (2, 12288)])
+def test_intersect_segmentation_variants(eng, cells: int, seg_cap: int) -> None:
+    """The multi-cell (large-sketch) path gives the same counts as the single-segment path."""
+    rng = np.random.default_rng(11)
+    from pyani_plus_b200 import engine
+
+    mh = engine.max_hash(100)
+    pool = np.unique(rng.integers(1, mh, 9000, dtype=np.uint64))
+    sketches = []
+    for i in range(13):
+        m = rng.random(len(pool)) < (0.15 + 0.05 * i)
+        sketches.append(pool[m])
+    sketches.append(np.empty(0, dtype=np.uint64))
+    sketches.append(pool[:1])
+    table = eng.table_from_host(sketches, 31, 100)
+    ov = eng.intersect(table, n_cells=cells, seg_cap=seg_cap).cpu().numpy()
+    for i, a in enumerate(sketches):
+        for j, b in enumerate(sketches):
+            assert ov[i, j] == len(np.intersect1d(a, b)), (i, j)
+
+
+def test_intersect_rectangular_and_sharded(eng) -> None:
+    """Queries x subjects (compute-column shape) and the rank/world split used on several GPUs."""
+    rng = np.random.default_rng(5)
+    from pyani_plus_b200 import engine
+
+    mh = engine.max_hash(1000)
+    pool = np.unique(rng.integers(1, mh, 4000, dtype=np.uint64))
+    sk = [pool[rng.random(len(pool)) < 0.5] for _ in range(21)]
+    q = eng.table_from_host(sk[:9], 31, 1000)
+    s = eng.table_from_host(sk[5:], 31, 1000)
+    ov = eng.intersect(q, s).cpu().numpy()
+    for i in range(9):
+        for j in range(16):
+            assert ov[i, j] == len(np.intersect1d(sk[i], sk[5 + j]))
+    full = eng.table_from_host(sk, 31, 1000)
+    whole = eng.intersect(full).cpu().numpy()
+    parts = sum(eng.intersect(full, rank=r, world=3).cpu().numpy().astype(np.int64) for r in range(3))
+    assert (parts == whole).all()
+    assert (whole == whole.T).all()
+    assert (np.diag(whole) == [len(x) for x in sk]).all()
+
+
+def test_full_size_genome_properties(eng) -> None:
+    """BASELINE-size genome (5 Mb, k=31, scaled=1000): size-independent properties.
+
+    * sketch(reverse complement) == sketch(genome)   (canonical k-mers)
+    * sketch is sorted, duplicate free, all values in (0, max_hash]
+    * a genome vs itself: |A n A| = |A|, ANI exactly 1.0
+    * sketch(A) u sketch(B) for a split with a k-1 overlap == sketch(A+B) as one record
+    """
+    from pyani_plus_b200 import engine
+
+    length = 5_000_000
+    seq = oracle.synth_genome(SEED, 0, length)
+    rc = seq.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+    cut = 2_345_678
+    table = eng.sketch_genomes([[seq], [rc], [seq[: cut + 30]], [seq[cut:]]], 31, 1000)
+    a, b, left, right = table.to_host()
+    assert a.tolist() == b.tolist()
+    assert (np.diff(a.astype(np.int64)) > 0).all()
+    assert a.min() > 0 and a.max() <= engine.max_hash(1000)
+    assert abs(len(a) - length / 1000) < 5 * (length / 1000) ** 0.5
+    assert np.union1d(left, right).tolist() == a.tolist()
+    ov = eng.intersect(table).cpu().numpy()
+    assert ov[0, 0] == len(a) and ov[0, 1] == len(a)
+    counts = table.counts.cpu().numpy()
+    ident, _ = engine.ani_host(ov.astype(np.uint32), counts, counts, 31)
+    assert ident[0, 1] == 1.0
+    assert ov[2, 3] == len(np.intersect1d(left, right))
