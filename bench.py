@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""Benchmark of the sourmash hot path (FracMinHash sketch + all-vs-all intersection -> ANI).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|config4|config5|tiny]
+    python bench.py --impl reference ...        # the CPU arm (oracle port on the host cores)
+
+One *step* = one pass of the hot path over one batch of synthetic genomes of the named BASELINE.json
+configuration: kernel K1 (hash + per-genome sort/dedup) over every genome, [all-gather of the
+sketches when N > 1], kernel K2 over every unordered genome pair, and the ANI kernel.
+
+* ``value``  whole-job genome pairs/s with the 2-bit packed genomes already resident in HBM.
+* ``e2e``    the same metric through the public engine API from HOST buffers: pinned ASCII genomes are
+             copied host->device, packed, sketched, intersected, and the two float64 ANI matrices are
+             copied back, all inside the timed region.
+* ``roofline``       dominant kernel of the step, algorithmic bytes / CUDA-event time vs measured HBM peak.
+* ``cpu_baseline``   the oracle (CPU port of the same algorithm) timed on the host cores (rank 0).
+
+Timing: CUDA events on the launching stream around every step (max over ranks), >= 3 warm-up steps,
+L2 flushed between steps by writing a 256 MiB buffer (outside the event pairs); the whole timed loop is
+bracketed by barrier + synchronize.  Multi-GPU (``torchrun``): strong scaling, genomes sliced across
+ranks for K1, one NCCL all-gather of the sketch rows, K2 work items dealt round-robin to ranks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SEED = 20261017
+METRIC = "all-vs-all genome pairs/sec + sketch Gbp/s (whole-job genome pairs/s; sketch Gbp/s in extra keys)"
+UNIT = "genome pairs/s"
+
+WORKLOADS = {
+    # name: (n_genomes, genome length, k, scaled, description from BASELINE.json configs[])
+    "tiny": (16, 200_000, 31, 1000, "16 synthetic 0.2 Mb genomes (self-test only)"),
+    "config2": (100, 5_000_000, 31, 1000, "configs[1]: 100 synthetic 5 Mb genomes, k=31, scaled=1000"),
+    "config3": (1000, 5_000_000, 31, 1000, "configs[2]: 1,000 synthetic 5 Mb genomes, k=31, scaled=1000"),
+    "config4": (10000, 5_000_000, 31, 1000, "configs[3]: 10,000 synthetic 5 Mb genomes, k=31, scaled=1000"),
+    "config5": (2000, 5_000_000, 31, 100, "configs[4]: 2,000 synthetic 5 Mb genomes, k=31, scaled=100"),
+}
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except (ValueError, KeyError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running beside the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self) -> None:
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)  # noqa: SIM115
+            self.path = f.name
+            self.proc = subprocess.Popen(  # noqa: S603
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in Path(self.path).read_text().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9], strict=True):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        Path(self.path).unlink(missing_ok=True)
+        # "under load" = samples in the upper half of what was seen
+        busy = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {
+            "sm_mhz": float(np.median(busy)) if busy else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ======================================================================================= CPU arm
+def cpu_measure(workload: str, steps: int, warmup: int, budget_s: float = 25.0) -> dict:
+    """Time the oracle port (all host threads) on a bounded sample of the workload.
+
+    Returns whole-job pairs/s extrapolated to the full workload: sketching scales linearly in the
+    number of genomes, intersection linearly in the number of pairs.
+    """
+    from oracle import oracle
+
+    n, length, k, scaled, _ = WORKLOADS[workload]
+    threads = oracle.num_threads()
+    n_pairs = n * (n - 1) // 2
+    # sample: enough genomes to keep every thread busy, bounded so a step stays within seconds
+    per_genome_s = length / 45e6  # ~45 Mbp/s/core for the scalar port
+    ns = int(max(4, min(n, threads * max(1, int(budget_s / max(1, steps + warmup) / per_genome_s)))))
+    ns = min(ns, 200)
+    seqs = np.empty((ns, length), dtype=np.uint8)
+    for g in range(ns):
+        seqs[g] = np.frombuffer(oracle.synth_genome(SEED, g, length), dtype=np.uint8)
+    cap = int(length / scaled * 1.5) + 256
+    out = np.zeros((ns, cap), dtype=np.uint64)
+    counts = np.zeros(ns, dtype=np.int64)
+    lib = oracle.lib()
+    t_sk, t_ix = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        lib.oracle_sketch_batch(seqs.ctypes.data, ns, length, k, oracle.max_hash(scaled),
+                                out.ctypes.data_as(oracle.c_u64p), cap, counts.ctypes.data_as(oracle.c_i64p))
+        t1 = time.perf_counter()
+        ov = oracle.intersect_all(out, counts)
+        t2 = time.perf_counter()
+        # ANI finalisation is part of the path
+        for i in range(min(ns, 64)):
+            oracle.pair_row(int(ov[0, i]), int(counts[0]), int(counts[i]), k)
+        if it >= warmup:
+            t_sk.append(t1 - t0)
+            t_ix.append(t2 - t1)
+    sk = float(np.mean(t_sk))
+    ix = float(np.mean(t_ix))
+    s_pairs = ns * (ns - 1) // 2
+    full_s = sk * (n / ns) + ix * (n_pairs / max(1, s_pairs))
+    return {
+        "value": n_pairs / full_s,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": (f"{ns} of {n} genomes sketched ({sk:.3f} s) and their {s_pairs} pairs intersected "
+                   f"({ix:.4f} s) per step, extrapolated linearly in genomes / pairs to the full workload"),
+        "sketch_gbp_s": ns * length / sk / 1e9,
+        "pairs_per_s_intersect": s_pairs / ix if ix > 0 else None,
+        "step_s": sk + ix,
+        "full_workload_s": full_s,
+    }
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, length, k, scaled, desc = WORKLOADS[args.workload]
+    base = cpu_measure(args.workload, args.steps, args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": base["full_workload_s"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled,
+                   "note": "pyani-plus's real CPU path (sourmash + branchwater, Rust) is not installable "
+                           "here; this arm times the oracle CPU port of the same algorithm with OpenMP"},
+        "cpu_baseline": {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
+        "sketch_gbp_s": base["sketch_gbp_s"],
+        "pairs_per_s_intersect": base["pairs_per_s_intersect"],
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================= GPU arm
+def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
+    import torch
+    import torch.distributed as dist
+
+    from pyani_plus_b200 import engine
+    from pyani_plus_b200 import stream as pstream
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = engine.Engine(local_rank)
+    dev = eng.device
+
+    n, length, k, scaled, desc = WORKLOADS[args.workload]
+    n_pairs = n * (n - 1) // 2
+    per_rank = -(-n // world)  # genomes sketched by each rank (last ranks may hold dummies)
+    g0 = rank * per_rank
+    n_local = max(0, min(n, g0 + per_rank) - g0)
+
+    # ---- inputs: this rank's slice of the genomes, generated on the device, then packed (resident)
+    # dummy genomes (length 0) pad the slice so that every rank gathers the same shape
+    tiles_per = length // pstream.TILE + 1
+    tile_off = np.zeros(per_rank + 1, dtype=np.int64)
+    for i in range(per_rank):
+        tile_off[i + 1] = tile_off[i] + (tiles_per if i < n_local else 1)
+    plan = eng.plan_stream(tile_off, scaled)
+    d_ascii = torch.full((plan.n_bases,), pstream.PAD, dtype=torch.uint8, device=dev)
+    if n_local:
+        real_bytes = n_local * tiles_per * pstream.TILE
+        gen, _ = eng.synth_ascii_stream(SEED, g0, n_local, length)
+        d_ascii[:real_bytes] = gen[:real_bytes]
+        del gen
+    bufs = eng.alloc_stream_buffers(plan, ascii_too=True)
+    eng.pack(d_ascii, plan, bufs)
+    tab = eng.alloc_table(plan)
+    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True)
+    h_ascii.copy_(d_ascii)
+    torch.cuda.synchronize()
+    del d_ascii
+
+    n_rows = per_rank * world
+    if world > 1:
+        all_rows = torch.empty((n_rows, plan.row_stride), dtype=torch.int64, device=dev)
+        all_counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    expected_max = int(length / scaled * 1.3) + 64  # sizing hint for K2's shared-memory plan
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    result = {}
+
+    def step(from_host: bool, marks: list | None = None) -> None:
+        """One pass of the hot path; optional event marks after each stage."""
+        if from_host:
+            eng.sketch_ascii_host(h_ascii, plan, bufs, tab, k)
+        else:
+            eng.sketch_packed(plan, bufs, tab, k)
+        if marks is not None:
+            marks[0].record()
+        if world > 1:
+            dist.all_gather_into_tensor(all_rows, tab["table"])
+            dist.all_gather_into_tensor(all_counts, tab["counts"])
+            table = engine.SketchTable(all_rows, all_counts, k, scaled)
+        else:
+            table = engine.SketchTable(tab["table"], tab["counts"], k, scaled)
+        if marks is not None:
+            marks[1].record()
+        ov = eng.intersect(table, rank=rank, world=world, max_count=expected_max)
+        if marks is not None:
+            marks[2].record()
+        ident, cov = eng.ani_device(ov, table)
+        if from_host:
+            result["identity"] = ident.cpu()
+            result["cov_query"] = cov.cpu()
+            result["counts"] = table.counts.cpu()
+        else:
+            result["ov"], result["table"] = ov, table
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(from_host: bool, steps: int, warmup: int) -> dict:
+        for _ in range(warmup):
+            step(from_host)
+            flush.fill_(1)
+        barrier()
+        launches0 = eng.launch_count()
+        tot, t_k1, t_gather, t_k2 = [], [], [], []
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            e0, e1 = ev(), ev()
+            marks = [ev(), ev(), ev()]
+            e0.record()
+            step(from_host, marks)
+            e1.record()
+            e1.synchronize()
+            tot.append(e0.elapsed_time(e1))
+            t_k1.append(e0.elapsed_time(marks[0]))
+            t_gather.append(marks[0].elapsed_time(marks[1]))
+            t_k2.append(marks[1].elapsed_time(marks[2]))
+            flush.fill_(1)  # L2 flush, outside the event pair
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if rank == 0 else None
+        launches = eng.launch_count() - launches0
+        stats = torch.tensor([sum(tot), sum(t_k1), sum(t_gather), sum(t_k2), float(launches)],
+                             dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = stats.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stats.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            stats = torch.cat([mx[:4], sm[4:]])
+        s = stats.cpu().tolist()
+        return {"ms": s[0] / steps, "k1_ms": s[1] / steps, "gather_ms": s[2] / steps, "k2_ms": s[3] / steps,
+                "launches": int(s[4]), "wall_s": wall, "clocks": clocks}
+
+    dev_t = timed_loop(False, args.steps, args.warmup)
+
+    # kernel-only timing of the dominant kernel (K1 hash) and of K2, alone on the stream
+    def time_kernel(fn, reps: int) -> float:
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = ev(), ev()
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    sk_args = eng._sketch_args(plan, bufs, tab, k, 42)  # noqa: SLF001
+    hash_args = sk_args[:12] + (sk_args[13], sk_args[14], sk_args[15])
+
+    def hash_only() -> None:
+        engine._check(eng.lib.panib_sketch_hash_only(*hash_args))  # noqa: SLF001
+
+    def finalize_only() -> None:
+        engine._check(eng.lib.panib_sketch_finalize(tab["table"].data_ptr(), plan.row_stride, plan.n_genomes,  # noqa: SLF001
+                                                    plan.d_nb.data_ptr(), tab["counts"].data_ptr(),
+                                                    tab["flags"].data_ptr(), eng._stream()))  # noqa: SLF001
+
+    reps = max(3, min(args.steps, 10))
+    k1_hash_ms = time_kernel(hash_only, reps)
+    finalize_only()
+    step(False)
+    table = result["table"]
+    k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world, max_count=expected_max), reps)
+    counts_host = table.counts.cpu().numpy()[:n].astype(np.int64)
+
+    e2e_t = timed_loop(True, max(2, args.steps // 2), 3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- derived numbers
+    peak, peak_src = hbm_peak()
+    local_bases = n_local * length
+    k1_bytes = local_bases * (0.25 + 0.125 + 8.0 / scaled)  # 2-bit stream + validity mask + hash writes
+    k1_gbs = k1_bytes / (k1_hash_ms * 1e-3) / 1e9
+    tot_cnt = int(counts_host.sum())
+    # K2 algorithmic bytes: sum over unordered pairs of 8(|A|+|B|) + 4 = 8 (n-1) sum|A| + 4 pairs
+    k2_bytes = (8.0 * (n - 1) * tot_cnt + 4.0 * n_pairs) / world
+    k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+    value = n_pairs / (dev_t["ms"] * 1e-3)
+    e2e_value = n_pairs / (e2e_t["ms"] * 1e-3)
+    dominant_is_k1 = dev_t["k1_ms"] >= dev_t["k2_ms"]
+    roof_k1 = {"kernel": "sketch_hash_kernel<31> (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peak,
+               "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
+               "ms_per_launch": k1_hash_ms, "bytes_per_bp": 0.25 + 0.125 + 8.0 / scaled,
+               "note": "integer-ALU bound by construction (MurmurHash3 over 31 ASCII bytes per base); see "
+                       "DESIGN.md and profiles/ for pipe utilisation"}
+    roof_k2 = {"kernel": "intersect_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+               "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k2_ms,
+               "bytes_per_pair": k2_bytes * world / max(1, n_pairs),
+               "note": "algorithmic bytes 8(|A|+|B|)+4 per pair; staged queries and L2-resident columns make "
+                       "DRAM traffic far smaller"}
+    cpu = cpu_measure(args.workload, 2, 1) if not args.no_cpu_baseline else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_t["ms"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled,
+                   "pairs": n_pairs, "seed": SEED, "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": f"genomes sliced over {world} rank(s) for K1, NCCL all-gather of sketch rows, "
+                                  "K2 work items round-robin" if world > 1 else "single GPU"},
+        "sketch_gbp_s": n * length / (dev_t["k1_ms"] * 1e-3) / 1e9,
+        "pairs_per_s_k2": n_pairs / (dev_t["k2_ms"] * 1e-3),
+        "stage_ms": {"k1_sketch": dev_t["k1_ms"], "allgather": dev_t["gather_ms"], "k2_intersect": dev_t["k2_ms"],
+                     "k1_hash_kernel_alone": k1_hash_ms, "k2_alone": k2_ms},
+        "roofline": roof_k1 if dominant_is_k1 else roof_k2,
+        "roofline_k1": roof_k1, "roofline_k2": roof_k2,
+        "cpu_baseline": ({k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "cpu_baseline_detail": ({"sketch_gbp_s": cpu["sketch_gbp_s"],
+                                 "pairs_per_s_intersect": cpu["pairs_per_s_intersect"]} if cpu else None),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_t["ms"],
+                "h2d_bytes_per_step": int(plan.n_bases) * world,
+                "d2h_bytes_per_step": int(2 * n_rows * n_rows * 8 + n_rows * 4) * world,
+                "stage_ms": {"h2d_pack_k1": e2e_t["k1_ms"], "allgather": e2e_t["gather_ms"],
+                             "k2_intersect": e2e_t["k2_ms"]}},
+        "gpu_launches": dev_t["launches"],
+        "clocks": dev_t["clocks"],
+        "sketch_sizes": {"mean": float(counts_host.mean()), "max": int(counts_host.max())},
+        "library": engine.library_version(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

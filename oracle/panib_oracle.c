@@ -153,6 +153,62 @@ ORACLE_API int64_t oracle_sketch(const uint8_t *seq, const int64_t *rec_offsets,
     return u;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Same sketch, engineered the way a production CPU implementation (sourmash's Rust core) does it:
+ * the record is upper-cased and reverse-complemented ONCE, the number of invalid bytes in the
+ * current window is kept rolling, and each k-mer costs one memcmp + one murmur.  This is the
+ * function the CPU *baseline* timings use (oracle_sketch above stays the naive checker; the two
+ * are compared on every fixture by tests/test_oracle_golden.py).
+ * ------------------------------------------------------------------------------------------- */
+ORACLE_API int64_t oracle_sketch_fast(const uint8_t *seq, const int64_t *rec_offsets, int64_t n_records,
+                                      int k, uint64_t max_hash, uint32_t seed,
+                                      uint64_t *out, int64_t cap) {
+    if (k < 1 || k > 255) return -1;
+    int64_t n = 0, alloc = 1024, maxlen = 0;
+    for (int64_t r = 0; r < n_records; r++) {
+        int64_t len = rec_offsets[r + 1] - rec_offsets[r];
+        if (len > maxlen) maxlen = len;
+    }
+    uint64_t *buf = (uint64_t *)malloc((size_t)alloc * 8);
+    uint8_t *up = (uint8_t *)malloc((size_t)maxlen + 1);
+    uint8_t *rc = (uint8_t *)malloc((size_t)maxlen + 1);
+    uint8_t *bad = (uint8_t *)malloc((size_t)maxlen + 1);
+    for (int64_t r = 0; r < n_records; r++) {
+        const uint8_t *s = seq + rec_offsets[r];
+        const int64_t len = rec_offsets[r + 1] - rec_offsets[r];
+        if (len < k) continue;
+        for (int64_t i = 0; i < len; i++) {
+            bad[i] = (uint8_t)!base_upper_valid(s[i], &up[i]);
+            rc[len - 1 - i] = bad[i] ? 'N' : comp_base(up[i]);
+        }
+        int64_t nbad = 0;
+        for (int j = 0; j < k - 1; j++) nbad += bad[j];
+        for (int64_t i = 0; i + k <= len; i++) {
+            nbad += bad[i + k - 1];
+            if (nbad == 0) {
+                const uint8_t *f = up + i, *c = rc + (len - i - k);
+                const uint8_t *canon = memcmp(f, c, (size_t)k) <= 0 ? f : c;
+                const uint64_t h = oracle_murmur64(canon, k, seed);
+                if (h != 0 && h <= max_hash) {
+                    if (n == alloc) { alloc *= 2; buf = (uint64_t *)realloc(buf, (size_t)alloc * 8); }
+                    buf[n++] = h;
+                }
+            }
+            nbad -= bad[i];
+        }
+    }
+    qsort(buf, (size_t)n, 8, cmp_u64);
+    int64_t u = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (i == 0 || buf[i] != buf[i - 1]) {
+            if (u < cap) out[u] = buf[i];
+            u++;
+        }
+    }
+    free(buf); free(up); free(rc); free(bad);
+    return u;
+}
+
 /* Exact |A n B| of two sorted, duplicate-free u64 lists (what manysearch calls intersect_hashes). */
 ORACLE_API int64_t oracle_intersect(const uint64_t *a, int64_t na, const uint64_t *b, int64_t nb) {
     int64_t i = 0, j = 0, c = 0;
@@ -253,7 +309,7 @@ ORACLE_API int64_t oracle_synth_sketch_batch(uint64_t seed, int64_t g0, int64_t 
         uint8_t *seq = (uint8_t *)malloc((size_t)length);
         oracle_synth_genome(seed, (uint64_t)(g0 + g), length, seq);
         int64_t offs[2] = {0, length};
-        counts[g] = oracle_sketch(seq, offs, 1, k, max_hash, 42, out + g * cap, cap);
+        counts[g] = oracle_sketch_fast(seq, offs, 1, k, max_hash, 42, out + g * cap, cap);
         free(seq);
     }
     return n_genomes * length;
@@ -265,7 +321,7 @@ ORACLE_API void oracle_sketch_batch(const uint8_t *seqs, int64_t n_genomes, int6
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t g = 0; g < n_genomes; g++) {
         int64_t offs[2] = {0, length};
-        counts[g] = oracle_sketch(seqs + g * length, offs, 1, k, max_hash, 42, out + g * cap, cap);
+        counts[g] = oracle_sketch_fast(seqs + g * length, offs, 1, k, max_hash, 42, out + g * cap, cap);
     }
 }
 

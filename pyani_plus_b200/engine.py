@@ -153,6 +153,23 @@ class SketchTable:
         return [rows[g, : counts[g]].copy() for g in range(self.n)]
 
 
+@dataclass
+class StreamPlan:
+    """Geometry + bucket plan of one tiled base stream (host and device copies)."""
+
+    tile_off: np.ndarray
+    n_genomes: int
+    n_tiles: int
+    n_bases: int
+    scaled: int
+    max_hash: int
+    slack: float
+    row_stride: int
+    d_tile_off: "torch.Tensor"  # noqa: F821, UP037
+    d_nb: "torch.Tensor"  # noqa: F821, UP037
+    d_bmul: "torch.Tensor"  # noqa: F821, UP037
+
+
 class Engine:
     """One engine per process / per GPU (``torch.cuda.current_device()``)."""
 
@@ -185,64 +202,101 @@ class Engine:
         return st
 
     # ------------------------------------------------------------------ stage 0+1: sketch
+    def plan_stream(self, tile_off: np.ndarray, scaled: int, slack: float = 1.0) -> "StreamPlan":
+        """Bucket plan + device copies of the per-genome arrays for one tiled base stream."""
+        torch = self.torch
+        tile_off = np.ascontiguousarray(tile_off, dtype=np.int64)
+        n_genomes = len(tile_off) - 1
+        nb = np.ones(max(n_genomes, 1), dtype=np.int32)
+        bmul = np.zeros(max(n_genomes, 1), dtype=np.uint64)
+        cache: dict[int, tuple[int, int]] = {}
+        for g in range(n_genomes):
+            tiles = int(tile_off[g + 1] - tile_off[g])
+            if tiles not in cache:
+                cache[tiles] = plan_buckets(tiles * _stream.TILE, scaled, slack)
+            nb[g], bmul[g] = cache[tiles]
+        return StreamPlan(
+            tile_off=tile_off, n_genomes=n_genomes, n_tiles=int(tile_off[-1]),
+            n_bases=(int(tile_off[-1]) + 1) * _stream.TILE, scaled=scaled, max_hash=max_hash(scaled),
+            slack=slack, row_stride=int(nb.max()) * 1024,
+            d_tile_off=torch.from_numpy(tile_off).to(self.device),
+            d_nb=torch.from_numpy(nb).to(self.device),
+            d_bmul=torch.from_numpy(bmul.view(np.int64)).to(self.device),
+        )
+
+    def alloc_stream_buffers(self, plan: "StreamPlan", *, ascii_too: bool = False) -> dict:
+        torch = self.torch
+        bufs = {
+            "packed": torch.empty(plan.n_bases // 16, dtype=torch.int32, device=self.device),
+            "mask": torch.empty(plan.n_bases // 32, dtype=torch.int32, device=self.device),
+        }
+        if ascii_too:
+            bufs["ascii"] = torch.empty(plan.n_bases, dtype=torch.uint8, device=self.device)
+        return bufs
+
+    def alloc_table(self, plan: "StreamPlan") -> dict:
+        torch = self.torch
+        n = max(plan.n_genomes, 1)
+        return {
+            "table": torch.empty((n, plan.row_stride), dtype=torch.int64, device=self.device),
+            "counts": torch.zeros(n, dtype=torch.int32, device=self.device),
+            "flags": torch.empty(n, dtype=torch.int32, device=self.device),
+        }
+
+    def pack(self, d_ascii, plan: "StreamPlan", bufs: dict) -> None:
+        """ASCII device stream -> packed 2-bit + mask (stage 0)."""
+        _check(self.lib.panib_pack_ascii(d_ascii.data_ptr(), plan.n_bases, bufs["packed"].data_ptr(),
+                                         bufs["mask"].data_ptr(), self._stream()))
+
+    def _sketch_args(self, plan: "StreamPlan", bufs: dict, tab: dict, k: int, seed: int) -> tuple:
+        return (bufs["packed"].data_ptr(), bufs["mask"].data_ptr(), plan.d_tile_off.data_ptr(), plan.n_genomes,
+                plan.n_tiles, k, seed, plan.max_hash, plan.d_nb.data_ptr(), plan.d_bmul.data_ptr(),
+                tab["table"].data_ptr(), plan.row_stride, tab["counts"].data_ptr(), tab["flags"].data_ptr(),
+                self.status.data_ptr(), self._stream())
+
+    def sketch_packed(self, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42) -> None:
+        """Kernel K1 on a device-resident packed stream (enqueue only; see ``check_status``)."""
+        _check(self.lib.panib_sketch_stream(*self._sketch_args(plan, bufs, tab, k, seed)))
+
+    def sketch_ascii_host(self, h_ascii, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *,
+                          seed: int = 42) -> None:
+        """H2D copy of a pinned ASCII stream + pack + K1 in one C-ABI call (enqueue only)."""
+        _check(self.lib.panib_sketch_ascii_host(h_ascii.data_ptr(), bufs["ascii"].data_ptr(), plan.n_bases,
+                                                *self._sketch_args(plan, bufs, tab, k, seed)))
+
+    def check_status(self) -> int:
+        """Synchronise and return (then clear) the PANIB_ST_* bits kernels raised."""
+        return self._read_status()
+
     def sketch_ascii_stream(
-        self, h_ascii, tile_off: np.ndarray, k: int, scaled: int, *, seed: int = 42, slack: float = 1.0,
-        from_host: bool = True, keep_buffers: dict | None = None,
+        self, ascii_stream, tile_off: np.ndarray, k: int, scaled: int, *, seed: int = 42, slack: float = 1.0,
+        from_host: bool = True,
     ) -> SketchTable:
         """Sketch every genome of one tiled ASCII base stream (``stream.py`` layout).
 
-        ``h_ascii`` is a pinned uint8 torch tensor when ``from_host`` (copied H2D inside the C call),
-        else a device tensor.  Retries with more buckets if a bucket overflowed.
+        ``ascii_stream`` is a pinned uint8 torch tensor when ``from_host`` (copied H2D inside the C
+        call), else a device tensor.  Retries with more buckets if a bucket overflowed.
         """
-        torch = self.torch
-        n_genomes = len(tile_off) - 1
-        n_tiles = int(tile_off[-1])
-        n_bases = (n_tiles + 1) * _stream.TILE
-        if h_ascii.numel() != n_bases:
-            msg = f"ASCII stream has {h_ascii.numel()} bytes, expected {n_bases}"
-            raise ValueError(msg)
-        mh = max_hash(scaled)
-        bufs = keep_buffers if keep_buffers is not None else {}
         while True:
-            nb = np.empty(n_genomes, dtype=np.int32)
-            bmul = np.empty(n_genomes, dtype=np.uint64)
-            for g in range(n_genomes):
-                n_kmers = int(tile_off[g + 1] - tile_off[g]) * _stream.TILE
-                nb[g], bmul[g] = plan_buckets(n_kmers, scaled, slack)
-            row_stride = int(nb.max()) * 1024 if n_genomes else 1024
-            d_tile_off = torch.from_numpy(tile_off.astype(np.int64)).to(self.device)
-            d_nb = torch.from_numpy(nb).to(self.device)
-            d_bmul = torch.from_numpy(bmul.view(np.int64)).to(self.device)
-            d_packed = bufs.get("packed")
-            if d_packed is None or d_packed.numel() != n_bases // 16:
-                d_packed = torch.empty(n_bases // 16, dtype=torch.int32, device=self.device)
-                d_mask = torch.empty(n_bases // 32, dtype=torch.int32, device=self.device)
-                bufs["packed"], bufs["mask"] = d_packed, d_mask
-            d_mask = bufs["mask"]
-            table = torch.empty((max(n_genomes, 1), row_stride), dtype=torch.int64, device=self.device)
-            counts = torch.zeros(max(n_genomes, 1), dtype=torch.int32, device=self.device)
-            flags = torch.empty(max(n_genomes, 1), dtype=torch.int32, device=self.device)
-            sk = (d_packed.data_ptr(), d_mask.data_ptr(), d_tile_off.data_ptr(), n_genomes, n_tiles, k, seed, mh,
-                  d_nb.data_ptr(), d_bmul.data_ptr(), table.data_ptr(), row_stride, counts.data_ptr(),
-                  flags.data_ptr(), self.status.data_ptr(), self._stream())
+            plan = self.plan_stream(tile_off, scaled, slack)
+            if ascii_stream.numel() != plan.n_bases:
+                msg = f"ASCII stream has {ascii_stream.numel()} bytes, expected {plan.n_bases}"
+                raise ValueError(msg)
+            bufs = self.alloc_stream_buffers(plan, ascii_too=from_host)
+            tab = self.alloc_table(plan)
             if from_host:
-                d_ascii = bufs.get("ascii")
-                if d_ascii is None or d_ascii.numel() != n_bases:
-                    d_ascii = torch.empty(n_bases, dtype=torch.uint8, device=self.device)
-                    bufs["ascii"] = d_ascii
-                _check(self.lib.panib_sketch_ascii_host(h_ascii.data_ptr(), d_ascii.data_ptr(), n_bases, *sk))
+                self.sketch_ascii_host(ascii_stream, plan, bufs, tab, k, seed=seed)
             else:
-                _check(self.lib.panib_pack_ascii(h_ascii.data_ptr(), n_bases, d_packed.data_ptr(),
-                                                 d_mask.data_ptr(), self._stream()))
-                _check(self.lib.panib_sketch_stream(*sk))
-            st = self._read_status()
+                self.pack(ascii_stream, plan, bufs)
+                self.sketch_packed(plan, bufs, tab, k, seed=seed)
+            st = self.check_status()
             if st & ST_BUCKET_OVERFLOW:
                 if slack > 64:
                     msg = "sketch buckets keep overflowing (more than 64x the expected number of hashes)"
                     raise EngineError(msg)
                 slack *= 2
                 continue
-            return SketchTable(table[:n_genomes], counts[:n_genomes], k, scaled)
+            return SketchTable(tab["table"][: plan.n_genomes], tab["counts"][: plan.n_genomes], k, scaled)
 
     def sketch_genomes(self, genomes: list[list[bytes]], k: int, scaled: int, *, seed: int = 42) -> SketchTable:
         """Sketch genomes given as lists of record sequences (what a FASTA parser yields).
@@ -263,13 +317,12 @@ class Engine:
         if genomes:
             batches.append((start, len(genomes)))
         parts: list[SketchTable] = []
-        bufs: dict = {}
         for b0, b1 in batches:
             tile_off = _stream.plan_tiles(lengths[b0:b1])
             nbytes = _stream.stream_bytes(tile_off)
             h_ascii = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             _stream.fill_ascii_stream(h_ascii.numpy(), tile_off, genomes[b0:b1])
-            parts.append(self.sketch_ascii_stream(h_ascii, tile_off, k, scaled, seed=seed, keep_buffers=bufs))
+            parts.append(self.sketch_ascii_stream(h_ascii, tile_off, k, scaled, seed=seed))
         return self.concat_tables(parts, k, scaled)
 
     def concat_tables(self, parts: list[SketchTable], k: int, scaled: int) -> SketchTable:

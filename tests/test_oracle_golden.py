@@ -85,6 +85,9 @@ def test_sig_files_bit_exact(golden: Path, sketches: dict, name: str) -> None:
         assert sig["ksize"] == 31
         assert sig["seed"] == 42
         assert got.tolist() == sig["mins"], f"{name}/{md5}"
+        recs = [s for _, s in oracle.fasta_records(oracle.read_bytes_maybe_gz(
+            next(f for f in _fasta_files(golden / name) if oracle.file_md5(f) == md5)))]
+        assert oracle.sketch_records(recs, 31, SETS[name], fast=True).tolist() == sig["mins"]
         assert len(got) == exp["sketch_sizes"][md5]
         assert oracle.sig_md5sum(got, 31) == sig["md5sum"]
     # every fixture FASTA has a .sig
@@ -158,6 +161,11 @@ def test_coverage_scaled50(golden: Path) -> None:
         md5: oracle.sketch_records([s for _, s in oracle.fasta_records(data)], 31, 50)
         for md5, data in files.items()
     }
+    for data in files.values():  # the engineered (baseline) form agrees with the naive checker
+        recs = [s for _, s in oracle.fasta_records(data)]
+        for k in (31, 21, 5):
+            assert (oracle.sketch_records(recs, k, 50, fast=True).tolist()
+                    == oracle.sketch_records(recs, k, 50).tolist())
     assert len(sk["154173fb8e7415ab45532a738572f957"]) == 148  # 149 if N-windows were hashed
     assert len(sk["a0efc718e680e34d2f5c8f5d2286ca9c"]) == 340
     assert len(sk["7b6a6226ce00e52edca15565aa0d270d"]) == 488
