@@ -63,56 +63,75 @@ def hbm_peak() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running beside the timed region."""
+    """Samples SM clock and throttle reasons through NVML from a thread beside the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {
+        "hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+        "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80,
+    }
 
-    def __init__(self, gpu_index: int) -> None:
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.path = None
+    def __init__(self, gpu_index: int, period_s: float = 0.002) -> None:
+        import threading
+
+        self.period = period_s
+        self.samples: list[tuple[int, int]] = []
+        self.sm_max = None
+        self.err = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        try:
+            import pynvml
+
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES remapping when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    phys = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = f"NVML unavailable: {e}"
+
+    def _run(self) -> None:
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                clk = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((clk, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
 
     def start(self) -> None:
-        try:
-            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)  # noqa: SIM115
-            self.path = f.name
-            self.proc = subprocess.Popen(  # noqa: S603
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+        if self.nv is not None:
+            self._thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in Path(self.path).read_text().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9], strict=True):
-                if val.lower().startswith("active"):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [self.err or "no NVML"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        clocks = [c for c, _ in self.samples]
+        reasons = set()
+        for _, rs in self.samples:
+            for name, bit in self.REASONS.items():
+                if rs & bit:
                     reasons.add(name)
-        Path(self.path).unlink(missing_ok=True)
-        # "under load" = samples in the upper half of what was seen
-        busy = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
         return {
-            "sm_mhz": float(np.median(busy)) if busy else None,
-            "sm_max_mhz": max(smax) if smax else None,
-            "samples": len(sm),
+            "sm_mhz": float(np.median(clocks)) if clocks else None,
+            "sm_max_mhz": self.sm_max,
+            "samples": len(clocks),
             "reasons": sorted(reasons),
         }
 

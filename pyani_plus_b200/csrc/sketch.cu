@@ -73,56 +73,94 @@ struct EmitToTable {
     }
 };
 
-// stage the tile (+halo) of the packed stream and of the mask into shared memory; find the genome.
-// Returns true when the tile holds at least one invalid base.
+// genome owning `tile`: largest g with tile_off[g] <= tile (all threads compute it redundantly; the
+// loads are uniform and L1-resident).  `g` is the previous answer, tried first.
+__device__ __forceinline__ int find_genome(const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile,
+                                           int g) {
+    if (tile >= __ldg(tile_off + g) && tile < __ldg(tile_off + g + 1)) return g;
+    int lo = 0, hi = n_genomes - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(tile_off + mid) <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronously stage one tile (+halo) of the packed stream and of the mask into shared memory
 template <int NWORDS, int NMASK>
-__device__ __forceinline__ bool stage_tile(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
-                                           const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile,
-                                           uint32_t *sp, uint32_t *sm, int *s_genome) {
-    const int tid = threadIdx.x;
-    const uint32_t *gp = packed + tile * (kTileBases / 16);
-    const uint32_t *gm = mask + tile * (kTileBases / 32);
-    for (int i = tid; i < NWORDS; i += blockDim.x) sp[i] = __ldg(gp + i);
-    uint32_t any = 0;
-    for (int i = tid; i < NMASK; i += blockDim.x) {
-        const uint32_t m = __ldg(gm + i);
-        sm[i] = m;
-        any |= m;
-    }
-    if (tid == 0) {  // largest g with tile_off[g] <= tile
-        int lo = 0, hi = n_genomes - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(tile_off + mid) <= tile) lo = mid; else hi = mid - 1;
-        }
-        *s_genome = lo;
-    }
-    return __syncthreads_or(any != 0u) != 0;
+__device__ __forceinline__ void prefetch_tile(const uint32_t *__restrict__ packed,
+                                              const uint32_t *__restrict__ mask, int64_t tile, uint32_t *sp,
+                                              uint32_t *sm) {
+    static_assert(NWORDS % 4 == 0 && NMASK % 4 == 0, "16-byte copies");
+    const uint32_t *gp = packed + tile * (kTileBases / 16);  // 1 KiB aligned
+    const uint32_t *gm = mask + tile * (kTileBases / 32);    // 512 B aligned
+    const int t = threadIdx.x;
+    if (t < NWORDS / 4) cp_async16(sp + 4 * t, gp + 4 * t);
+    else if (t < NWORDS / 4 + NMASK / 4) cp_async16(sm + 4 * (t - NWORDS / 4), gm + 4 * (t - NWORDS / 4));
+    cp_async_commit();
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1, register-resident form for compile-time K <= 32 (see kmer_hash.cuh for the thread geometry)
+// K1, register-resident form for compile-time K <= 32 (see kmer_hash.cuh for the thread geometry).
+// Persistent CTAs (grid = SMs x resident CTAs) walk the tiles with stride gridDim.x; the next tile
+// is prefetched with cp.async into the other half of a double buffer while the current one is
+// hashed, so the ALU pipes never wait for HBM.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kThreadsK1, 2)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
-                   const int64_t *__restrict__ tile_off, int n_genomes, uint32_t seed, uint64_t max_hash,
-                   const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
+                   const int64_t *__restrict__ tile_off, int n_genomes, int64_t n_tiles, uint32_t seed,
+                   uint64_t max_hash, const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
                    uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
-    __shared__ __align__(16) uint32_t sp[kTileWords];
-    __shared__ __align__(16) uint32_t sm[kTileMaskWords];
-    __shared__ int s_genome;
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
-    const bool dirty = stage_tile<kTileWords, kTileMaskWords>(packed, mask, tile_off, n_genomes, tile, sp, sm,
-                                                              &s_genome);
-    const int g = s_genome;
-    EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g, status};
+    __shared__ __align__(16) uint32_t sp[2][kTileWords];
+    __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
+    int64_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    prefetch_tile<kTileWords, kTileMaskWords>(packed, mask, tile, sp[0], sm[0]);
     const int u = threadIdx.x >> 2, a = threadIdx.x & 3;
-    if (!dirty) {
-        hash_thread_kmers<K, false>(sp, sm, u, a, seed, emit);
-    } else {
-        hash_thread_kmers<K, true>(sp, sm, u, a, seed, emit);
+    int g = 0;
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) {
+            prefetch_tile<kTileWords, kTileMaskWords>(packed, mask, next, sp[cur ^ 1], sm[cur ^ 1]);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // every thread's copies of the current tile have landed
+        const uint32_t m = threadIdx.x < kTileMaskWords ? sm[cur][threadIdx.x] : 0u;
+        const bool dirty = __syncthreads_or(m != 0u) != 0;
+        g = find_genome(tile_off, n_genomes, tile, g);
+        EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g,
+                         status};
+        if (!dirty) {
+            hash_thread_kmers<K, false>(sp[cur], sm[cur], u, a, seed, emit);
+        } else {
+            hash_thread_kmers<K, true>(sp[cur], sm[cur], u, a, seed, emit);
+        }
+        __syncthreads();  // the buffer is overwritten by the prefetch of the next iteration
     }
+}
+
+// synchronous staging used by the generic kernel
+template <int NWORDS, int NMASK>
+__device__ __forceinline__ void stage_tile(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                                           int64_t tile, uint32_t *sp, uint32_t *sm) {
+    const int tid = threadIdx.x;
+    const uint32_t *gp = packed + tile * (kTileBases / 16);
+    const uint32_t *gm = mask + tile * (kTileBases / 32);
+    for (int i = tid; i < NWORDS; i += blockDim.x) sp[i] = __ldg(gp + i);
+    for (int i = tid; i < NMASK; i += blockDim.x) sm[i] = __ldg(gm + i);
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -138,15 +176,16 @@ __device__ __forceinline__ uint32_t base_at(const uint32_t *sp, int pos) {
 
 __global__ void __launch_bounds__(256)
 sketch_hash_generic_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
-                           const int64_t *__restrict__ tile_off, int n_genomes, int k, uint32_t seed,
-                           uint64_t max_hash, const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
-                           uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
+                           const int64_t *__restrict__ tile_off, int n_genomes, int64_t n_tiles, int k,
+                           uint32_t seed, uint64_t max_hash, const int32_t *__restrict__ nb,
+                           const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
+                           int32_t *flags, int32_t *status) {
     __shared__ uint32_t sp[kGenWords];
     __shared__ uint32_t sm[kGenMask];
-    __shared__ int s_genome;
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
-    stage_tile<kGenWords, kGenMask>(packed, mask, tile_off, n_genomes, tile, sp, sm, &s_genome);
-    const int g = s_genome;
+    if (tile >= n_tiles) return;
+    stage_tile<kGenWords, kGenMask>(packed, mask, tile, sp, sm);
+    const int g = find_genome(tile_off, n_genomes, tile, 0);
     EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g, status};
     const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
     const uint32_t lut = 0x54474341u;
@@ -246,10 +285,26 @@ sketch_finalize_kernel(uint64_t *__restrict__ table, int64_t row_stride, const i
 // ================================================================================================
 using namespace panib;
 
-static dim3 tile_grid(int64_t n_tiles) {
-    const int64_t gx = n_tiles < 65536 * 16 ? n_tiles : 65536 * 16;
+static dim3 tile_grid(int64_t n_tiles) {  // one CTA per tile (generic kernel); surplus CTAs exit
+    const int64_t gx = n_tiles < (1 << 30) ? n_tiles : (1 << 30);
     const int64_t gy = (n_tiles + gx - 1) / gx;
     return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+// persistent grid of the fast kernel: SMs x resident CTAs per SM
+template <int K>
+static int persistent_grid(int64_t n_tiles) {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, sms = 148, per_sm = 2;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K>, kThreadsK1, 0) !=
+                cudaSuccess || per_sm < 1)
+            per_sm = 2;
+        cached = sms * per_sm;
+    }
+    return (int)(n_tiles < cached ? n_tiles : cached);
 }
 
 extern "C" int panib_pack_ascii(const uint8_t *d_ascii, int64_t n_bases, uint32_t *d_packed, uint32_t *d_mask,
@@ -283,22 +338,18 @@ extern "C" int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *
     cudaStream_t st = (cudaStream_t)stream;
     PANIB_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
     PANIB_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
-    const dim3 grid = tile_grid(n_tiles);
-    if ((int64_t)grid.x * grid.y != n_tiles) {
-        set_error("n_tiles=%lld cannot be tiled into a grid", (long long)n_tiles);
-        return PANIB_E_ARG;
-    }
-#define PANIB_LAUNCH_K(KK)                                                                                    \
-    sketch_hash_kernel<KK><<<grid, kThreadsK1, 0, st>>>(d_packed, d_mask, d_tile_off, (int)n_genomes, seed,   \
-                                                         max_hash, d_nb, d_bmul, d_table, row_stride, d_flags, \
-                                                         d_status)
+#define PANIB_LAUNCH_K(KK)                                                                                   \
+    sketch_hash_kernel<KK><<<persistent_grid<KK>(n_tiles), kThreadsK1, 0, st>>>(                              \
+        d_packed, d_mask, d_tile_off, (int)n_genomes, n_tiles, seed, max_hash, d_nb, d_bmul, d_table,        \
+        row_stride, d_flags, d_status)
     switch (k) {
     case 21: PANIB_LAUNCH_K(21); break;
     case 31: PANIB_LAUNCH_K(31); break;
     default:
-        sketch_hash_generic_kernel<<<grid, 256, 0, st>>>(d_packed, d_mask, d_tile_off, (int)n_genomes, k, seed,
-                                                         max_hash, d_nb, d_bmul, d_table, row_stride, d_flags,
-                                                         d_status);
+        sketch_hash_generic_kernel<<<tile_grid(n_tiles), 256, 0, st>>>(d_packed, d_mask, d_tile_off,
+                                                                        (int)n_genomes, n_tiles, k, seed, max_hash,
+                                                                        d_nb, d_bmul, d_table, row_stride, d_flags,
+                                                                        d_status);
     }
 #undef PANIB_LAUNCH_K
     return check_launch("sketch_hash_kernel");
