@@ -134,11 +134,30 @@ PANIB_HD U64 rotl(U64 x) {
 }
 
 PANIB_HD U64 add64(U64 a, U64 b) {
+#if defined(__CUDA_ARCH__) && defined(PANIB_ADD_FMA)
+    // 64-bit add as IMAD.WIDE (a.lo * 1 + b) + IMAD (a.hi * 1 + carry-in high word): FMA pipe, not ALU pipe
+    uint32_t plo, phi, rhi;
+    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 q, {%3, %4};\n\tmad.wide.u32 p, %2, 1, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=r"(plo), "=r"(phi) : "r"(a.lo), "r"(b.lo), "r"(b.hi));
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(rhi) : "r"(a.hi), "r"(phi));
+    return U64{plo, rhi};
+#else
     const uint64_t r = to_u64(a) + to_u64(b);
     return U64{(uint32_t)r, (uint32_t)(r >> 32)};
+#endif
 }
 PANIB_HD U64 xor64(U64 a, U64 b) { return U64{a.lo ^ b.lo, a.hi ^ b.hi}; }
-PANIB_HD U64 xorshift33(U64 x) { return U64{x.lo ^ (x.hi >> 1), x.hi}; }  // x ^= x >> 33
+PANIB_HD U64 xorshift33(U64 x) {  // x ^= x >> 33
+#if defined(__CUDA_ARCH__) && defined(PANIB_XS_WIDE)
+    // hi >> 1 as the upper half of hi * 2^31 (IMAD.WIDE on the FMA pipe instead of SHF on the ALU pipe)
+    uint32_t s, dummy;
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, 0x80000000;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=r"(dummy), "=r"(s) : "r"(x.hi));
+    return U64{x.lo ^ s, x.hi};
+#else
+    return U64{x.lo ^ (x.hi >> 1), x.hi};
+#endif
+}
 PANIB_HD U64 fmix(U64 k) {
     k = xorshift33(k);
     k = mul_const<0xff51afd7ed558ccdULL>(k);
@@ -275,18 +294,28 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, i
         Xr[w] = sh ? shf_r(l, h, sh) : l;
     }
 
-    // ASCII expansion of both strands (each base expanded once per thread)
+    // ASCII expansion of both strands: each base is expanded once per thread, but LAZILY -- one packed
+    // word (4 ASCII registers) of each strand right before the first k-mer that needs it -- so that
+    // only ~NWD+4 ASCII registers per strand are live at a time (register pressure decides how many
+    // warps are resident, and K1 is latency bound: more warps = more throughput).
     uint32_t G[4 * NX], H[4 * NX];
 #pragma unroll
-    for (int w = 0; w < NX; w++) {
-        if (4 * w < NA) {
-            expand16(X[w], &G[4 * w]);
-            expand16(Xr[w], &H[4 * w]);
-        }
-    }
-
-#pragma unroll
     for (int j = 0; j < kKmersPerThread; j++) {
+        // forward strand: k-mer j reads G[j .. j+NWD)
+        {
+            const int hi_w = (j + NWD - 1) >> 2;               // last packed word needed by this k-mer
+            const int lo_w = j == 0 ? 0 : ((j + NWD - 2) >> 2) + 1;  // first word not yet expanded
+#pragma unroll
+            for (int w = lo_w; w <= hi_w; w++) expand16(X[w], &G[4 * w]);
+        }
+        // reverse strand: k-mer j reads H[15-j .. 15-j+NWD)
+        {
+            const int b = kKmersPerThread - 1 - j;
+            const int lo_w = b >> 2;
+            const int hi_w = j == 0 ? (b + NWD - 1) >> 2 : ((b + 1) >> 2) - 1;  // words below the previous k-mer's
+#pragma unroll
+            for (int w = lo_w; w <= hi_w; w++) expand16(Xr[w], &H[4 * w]);
+        }
         bool valid = true;
         if (DIRTY) {
             const int pos = 64 * u + a + 4 * j;
@@ -303,6 +332,7 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, i
         const uint64_t h = murmur_words<K>(W, seed);
         if (!DIRTY || valid) emit(h);
     }
+    (void)NA;
 }
 
 }  // namespace panib

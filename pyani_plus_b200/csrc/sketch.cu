@@ -68,8 +68,10 @@ struct EmitToTable {
     int32_t *flag;
     int32_t *status;
     __device__ __forceinline__ void operator()(uint64_t h) const {
-        // keep iff 0 < h <= max_hash (sourmash skips hash 0)
-        if (h - 1ull < max_hash) table_insert(row, nb, bmul, h, flag, status);
+        // keep iff 0 < h <= max_hash (sourmash skips hash 0; tested on the rare path only)
+        if (h <= max_hash) {
+            if (h != 0ull) table_insert(row, nb, bmul, h, flag, status);
+        }
     }
 };
 
@@ -94,49 +96,52 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// asynchronously stage one tile (+halo) of the packed stream and of the mask into shared memory
-template <int NWORDS, int NMASK>
-__device__ __forceinline__ void prefetch_tile(const uint32_t *__restrict__ packed,
-                                              const uint32_t *__restrict__ mask, int64_t tile, uint32_t *sp,
-                                              uint32_t *sm) {
-    static_assert(NWORDS % 4 == 0 && NMASK % 4 == 0, "16-byte copies");
-    const uint32_t *gp = packed + tile * (kTileBases / 16);  // 1 KiB aligned
-    const uint32_t *gm = mask + tile * (kTileBases / 32);    // 512 B aligned
-    const int t = threadIdx.x;
-    if (t < NWORDS / 4) cp_async16(sp + 4 * t, gp + 4 * t);
-    else if (t < NWORDS / 4 + NMASK / 4) cp_async16(sm + 4 * (t - NWORDS / 4), gm + 4 * (t - NWORDS / 4));
-    cp_async_commit();
-}
-
 // ------------------------------------------------------------------------------------------------
 // K1, register-resident form for compile-time K <= 32 (see kmer_hash.cuh for the thread geometry).
 // Persistent CTAs (grid = SMs x resident CTAs) walk the tiles with stride gridDim.x; the next tile
 // is prefetched with cp.async into the other half of a double buffer while the current one is
-// hashed, so the ALU pipes never wait for HBM.
+// hashed.  __launch_bounds__(256, 4) keeps the kernel at <= 64 registers (lazy ASCII expansion in
+// kmer_hash.cuh makes that spill-free): K1 is bound by the ALU pipe, and 32 resident warps per SM
+// measured 8 % faster than 16 (ncu: profiles/).  A warp-private-tile variant without CTA barriers
+// was measured 6 % SLOWER (its warps drift apart and the 40 KB unrolled body thrashes the
+// instruction cache), so tiles stay CTA-wide.
 // ------------------------------------------------------------------------------------------------
+#ifndef PANIB_K1_MINBLOCKS
+#define PANIB_K1_MINBLOCKS 4
+#endif
 template <int K>
-__global__ void __launch_bounds__(kThreadsK1, 2)
+__global__ void __launch_bounds__(kThreadsK1, PANIB_K1_MINBLOCKS)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
                    const int64_t *__restrict__ tile_off, int n_genomes, int64_t n_tiles, uint32_t seed,
                    uint64_t max_hash, const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
                    uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
+    // CTA-sized tiles (variant 0): persistent CTAs, double buffer, two barriers per tile
     __shared__ __align__(16) uint32_t sp[2][kTileWords];
     __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
     int64_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
-    prefetch_tile<kTileWords, kTileMaskWords>(packed, mask, tile, sp[0], sm[0]);
+    auto prefetch = [&](int64_t t, int b) {
+        const uint32_t *gp = packed + t * (kTileBases / 16);
+        const uint32_t *gm = mask + t * (kTileBases / 32);
+        const int x = threadIdx.x;
+        if (x < kTileWords / 4) cp_async16(sp[b] + 4 * x, gp + 4 * x);
+        else if (x < kTileWords / 4 + kTileMaskWords / 4)
+            cp_async16(sm[b] + 4 * (x - kTileWords / 4), gm + 4 * (x - kTileWords / 4));
+        cp_async_commit();
+    };
+    prefetch(tile, 0);
     const int u = threadIdx.x >> 2, a = threadIdx.x & 3;
     int g = 0;
     for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
         const int cur = it & 1;
         const int64_t next = tile + gridDim.x;
         if (next < n_tiles) {
-            prefetch_tile<kTileWords, kTileMaskWords>(packed, mask, next, sp[cur ^ 1], sm[cur ^ 1]);
+            prefetch(next, cur ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();  // every thread's copies of the current tile have landed
+        __syncthreads();
         const uint32_t m = threadIdx.x < kTileMaskWords ? sm[cur][threadIdx.x] : 0u;
         const bool dirty = __syncthreads_or(m != 0u) != 0;
         g = find_genome(tile_off, n_genomes, tile, g);
@@ -147,7 +152,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         } else {
             hash_thread_kmers<K, true>(sp[cur], sm[cur], u, a, seed, emit);
         }
-        __syncthreads();  // the buffer is overwritten by the prefetch of the next iteration
+        __syncthreads();
     }
 }
 

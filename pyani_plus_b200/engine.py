@@ -46,13 +46,16 @@ def load_library() -> ctypes.CDLL:
     global _lib  # noqa: PLW0603
     if _lib is not None:
         return _lib
-    if not LIB_PATH.is_file():
+    import os  # noqa: PLC0415
+
+    lib_path = Path(os.environ.get("PANIB200_LIB", LIB_PATH))  # override = kernel-variant experiments
+    if not lib_path.is_file():
         msg = (
-            f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            f"{lib_path} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`."
             " There is no CPU fallback for the sourmash path."
         )
         raise EngineError(msg)
-    L = ctypes.CDLL(str(LIB_PATH))
+    L = ctypes.CDLL(str(lib_path))
     L.panib_version.restype = ctypes.c_char_p
     L.panib_last_error.restype = _i32
     L.panib_last_error.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
