@@ -284,7 +284,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             table = engine.SketchTable(tab["table"], tab["counts"], k, scaled)
         if marks is not None:
             marks[1].record()
-        ov = eng.intersect(table, rank=rank, world=world, max_count=expected_max)
+        ov = eng.intersect(table, rank=rank, world=world)
         if marks is not None:
             marks[2].record()
         ident, cov = eng.ani_device(ov, table)
@@ -372,7 +372,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     finalize_only()
     step(False)
     table = result["table"]
-    k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world, max_count=expected_max), reps)
+    k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world), reps)
     counts_host = table.counts.cpu().numpy()[:n].astype(np.int64)
 
     e2e_t = timed_loop(True, max(2, args.steps // 2), 3)

@@ -77,7 +77,14 @@ diag_kernel(const int32_t *__restrict__ counts, int n, uint32_t *__restrict__ ov
     if (i < n) ov[(size_t)i * ld + i] = (uint32_t)counts[i];
 }
 
-__global__ void __launch_bounds__(256) intersect_kernel(const K2Args a) {
+constexpr int kThreadsK2 = 512;
+constexpr uint32_t kIdxMany = 0x8000u;  // flag in an index entry: the bucket holds more than 2 elements
+
+__device__ __forceinline__ uint32_t k2_bucket(uint64_t x, uint64_t base, int pre, uint32_t mul) {
+    return __umulhi((uint32_t)((x - base) >> pre), mul);
+}
+
+__global__ void __launch_bounds__(kThreadsK2) intersect_kernel(const K2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *seg = reinterpret_cast<uint64_t *>(smem_raw);
     uint16_t *idx = reinterpret_cast<uint16_t *>(seg + a.seg_cap);
@@ -108,28 +115,41 @@ __global__ void __launch_bounds__(256) intersect_kernel(const K2Args a) {
         q0 = a.q_fence[(size_t)i * (a.G + 1) + c];
         q1 = a.q_fence[(size_t)i * (a.G + 1) + c + 1];
     }
+    // the all-ones hash (possible only when max_hash == 2^64-1) doubles as the shared-memory
+    // sentinel, so it is stripped from both lists and counted on its own
+    const bool q_ones = q1 > q0 && qrow[q1 - 1] == kEmpty;
+    if (q_ones) --q1;
     const int n = q1 - q0;
-    if (n > a.seg_cap) {
+    if (n + 2 > a.seg_cap) {
         if (tid == 0) atomicOr(a.status, PANIB_ST_SEGMENT_OVERFLOW);
         return;
     }
-    if (n <= 0) return;  // ov was zero-initialised
     const uint64_t base = a.G > 1 ? (uint64_t)c * a.cellw : 0ull;
     const int pre = a.pre;
     const uint32_t mul = a.mul;
-    for (int p = tid; p < n; p += blockDim.x) seg[p] = qrow[q0 + p];
+    const int R = a.R;
+    for (int p = tid; p < n + 2; p += kThreadsK2) seg[p] = p < n ? qrow[q0 + p] : kEmpty;
     __syncthreads();
-    for (int p = tid; p < n; p += blockDim.x) {
-        const int b = (int)__umulhi((uint32_t)((seg[p] - base) >> pre), mul);
-        const int bprev = p > 0 ? (int)__umulhi((uint32_t)((seg[p - 1] - base) >> pre), mul) : -1;
+    // idx[b] = first position whose bucket is >= b (every entry is written exactly once)
+    for (int p = tid; p < n; p += kThreadsK2) {
+        const int b = (int)k2_bucket(seg[p], base, pre, mul);
+        const int bprev = p > 0 ? (int)k2_bucket(seg[p - 1], base, pre, mul) : -1;
         for (int q = bprev + 1; q <= b; q++) idx[q] = (uint16_t)p;
-        if (p == n - 1)
-            for (int q = b + 1; q <= a.R; q++) idx[q] = (uint16_t)n;
+    }
+    {
+        const int blast = n > 0 ? (int)k2_bucket(seg[n - 1], base, pre, mul) : -1;
+        for (int q = blast + 1 + tid; q <= R; q += kThreadsK2) idx[q] = (uint16_t)n;
+    }
+    __syncthreads();
+    for (int q = tid; q < R; q += kThreadsK2) {  // flag the buckets with more than two elements
+        const uint32_t lo = idx[q] & 0x7FFFu, hi = idx[q + 1] & 0x7FFFu;
+        if (hi - lo > 2u) idx[q] = (uint16_t)(lo | kIdxMany);
     }
     __syncthreads();
 
-    // ---- each warp streams subject columns and probes the staged query
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // ---- each warp streams subject columns (sorted, so neighbouring lanes probe neighbouring slots)
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kThreadsK2 / 32;
     for (int col = j0 + warp; col < j1; col += nwarps) {
         const uint64_t *srow = a.s_rows + (size_t)col * a.s_stride;
         int s0 = 0, s1 = a.s_counts[col];
@@ -138,16 +158,28 @@ __global__ void __launch_bounds__(256) intersect_kernel(const K2Args a) {
             s1 = a.s_fence[(size_t)col * (a.G + 1) + c + 1];
         }
         uint32_t cnt = 0;
-        for (int p = s0 + lane; p < s1; p += 32) {
-            const uint64_t x = __ldg(srow + p);
-            const uint32_t b = __umulhi((uint32_t)((x - base) >> pre), mul);
-            uint32_t lo = idx[b];
-            const uint32_t hi = idx[b + 1];
-            while (lo < hi) {
-                cnt += (seg[lo] == x) ? 1u : 0u;
-                ++lo;
-            }
+        if (s1 > s0 && __ldg(srow + s1 - 1) == kEmpty) {
+            --s1;
+            cnt = (lane == 0 && q_ones) ? 1u : 0u;
         }
+        auto probe = [&](uint64_t x) {
+            const uint32_t b = k2_bucket(x, base, pre, mul);
+            const uint32_t e = idx[b];
+            const uint32_t lo = e & 0x7FFFu;
+            cnt += (seg[lo] == x) ? 1u : 0u;
+            cnt += (seg[lo + 1] == x) ? 1u : 0u;
+            if (e & kIdxMany) {  // rare: walk the rest of a crowded bucket
+                const uint32_t hi = idx[b + 1] & 0x7FFFu;
+                for (uint32_t q = lo + 2; q < hi; q++) cnt += (seg[q] == x) ? 1u : 0u;
+            }
+        };
+        int p = s0 + lane;
+        for (; p + 96 < s1; p += 128) {  // four independent loads in flight per lane
+            const uint64_t x0 = __ldg(srow + p), x1 = __ldg(srow + p + 32), x2 = __ldg(srow + p + 64),
+                           x3 = __ldg(srow + p + 96);
+            probe(x0); probe(x1); probe(x2); probe(x3);
+        }
+        for (; p < s1; p += 32) probe(__ldg(srow + p));
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
         if (lane == 0) {
             if (a.G > 1) {
@@ -218,14 +250,22 @@ int bitlen64(uint64_t v) {
 }
 
 // choose segmentation and the bucket map; 0 values mean "choose for me"
+//   seg_cap : elements of a query segment staged in shared memory (+2 sentinels), <= 32767
+//   R       : index buckets, ~3 per element (0.33 elements per bucket on average)
+// Auto policy: one segment when the largest sketch has <= 6144 hashes (<= ~75 KB of shared memory,
+// three CTAs per SM); larger sketches are cut into value cells of ~4900 hashes.
 K2Plan make_plan(uint64_t max_hash, int64_t max_count, int n_cells, int seg_cap, int idx_buckets) {
     K2Plan p;
-    if (seg_cap <= 0) seg_cap = max_count <= 6144 ? 6144 : 12288;
-    if (idx_buckets <= 0) idx_buckets = seg_cap <= 6144 ? 16384 : 32768;
-    if (n_cells <= 0) {
-        n_cells = 1;
-        if (max_count > seg_cap) n_cells = (int)((max_count * 4 + 3 * (int64_t)seg_cap - 1) / (3 * (int64_t)seg_cap));
+    if (max_count < 1) max_count = 1;
+    if (n_cells <= 0) n_cells = max_count <= 6144 ? 1 : (int)((max_count * 5 + 4 * 6144 - 1) / (4 * 6144));
+    if (seg_cap <= 0) {
+        // expected cell population + 6 sigma (cells are equal slices of a uniform hash range)
+        const double mean = (double)max_count / n_cells;
+        const double want = n_cells == 1 ? (double)max_count : mean + 6.0 * sqrt(mean) + 16.0;
+        seg_cap = (int)((int64_t)(want + 2 + 63) / 64 * 64);
     }
+    if (seg_cap > 32767) seg_cap = 32767;
+    if (idx_buckets <= 0) idx_buckets = 3 * seg_cap;
     p.G = n_cells;
     p.seg_cap = seg_cap;
     p.R = idx_buckets;
@@ -237,6 +277,7 @@ K2Plan make_plan(uint64_t max_hash, int64_t max_count, int n_cells, int seg_cap,
     const int bl = bitlen64(vmax_full);
     p.pre = bl > 32 ? bl - 32 : 0;
     const uint64_t vmax = vmax_full >> p.pre;  // < 2^32
+    // bucket(v) = floor(v * mul / 2^32) with mul <= 2^32 * R / (vmax + 1): monotone, < R
     unsigned __int128 m = (((unsigned __int128)p.R) << 32) / ((unsigned __int128)vmax + 1);
     if (m > 0xFFFFFFFFull) m = 0xFFFFFFFFull;
     p.mul = (uint32_t)m;
@@ -268,7 +309,7 @@ extern "C" int panib_intersect(const uint64_t *d_q_rows, const int32_t *d_q_coun
     }
     cudaStream_t st = (cudaStream_t)stream;
     const K2Plan p = make_plan(max_hash, max_count, n_cells, seg_cap, idx_buckets);
-    if (p.seg_cap > 65535 || p.R > 65535 * 4 || p.seg_cap < 1) {
+    if (p.seg_cap > 32767 || p.seg_cap < 3 || p.R < 1) {
         set_error("panib_intersect: seg_cap=%d / idx_buckets=%d out of range", p.seg_cap, p.R);
         return PANIB_E_ARG;
     }
@@ -315,11 +356,12 @@ extern "C" int panib_intersect(const uint64_t *d_q_rows, const int32_t *d_q_coun
         }
     }
 
-    // columns per work item: aim for a few thousand items so that 148 SMs x 2 CTAs stay busy
+    // columns per work item (16 warps, one column each at a time): aim for a few thousand items so
+    // that 148 SMs x 3 CTAs stay busy, while a staged query is re-used by as many columns as possible
     const double pairs = (double)nq * (double)ns * (symmetric ? 0.5 : 1.0) * p.G / (double)world;
-    int JB = (int)(pairs / 2400.0);
-    JB = JB < 8 ? 8 : (JB > 128 ? 128 : JB);
-    JB = (JB + 7) & ~7;
+    int JB = (int)(pairs / 3600.0);
+    JB = JB < 16 ? 16 : (JB > 256 ? 256 : JB);
+    JB = (JB + 15) & ~15;
     a.JB = JB;
     a.nJB = (int)((ns + JB - 1) / JB);
     int SB = 1024 / JB;  // ~1024 columns (a few tens of MB of sketches) per L2 super-block
@@ -331,7 +373,7 @@ extern "C" int panib_intersect(const uint64_t *d_q_rows, const int32_t *d_q_coun
     const int64_t gx = items < (1 << 30) ? items : (1 << 30);
     const int64_t gy = (items + gx - 1) / gx;
     // (ids >= items decode to a column block >= nJB and exit immediately)
-    intersect_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, smem, st>>>(a);
+    intersect_kernel<<<dim3((unsigned)gx, (unsigned)gy), kThreadsK2, smem, st>>>(a);
     int rc = check_launch("intersect_kernel");
     if (rc) return rc;
     if (symmetric && rank == 0) {

@@ -47,8 +47,8 @@ assert eng.check_status() == 0
 table = engine.SketchTable(tab["table"], tab["counts"], k, scaled)
 chk = int(table.counts.sum().item())
 mc = int(length / scaled * 1.3) + 64
-t_k2 = timeit(lambda: eng.intersect(table, max_count=mc))
-ov = eng.intersect(table, max_count=mc)
+t_k2 = timeit(lambda: eng.intersect(table))
+ov = eng.intersect(table)
 print(f"{workload} hash {t_hash[0]:.3f} ms (min {t_hash[1]:.3f}) = {n*length/t_hash[0]/1e6:.1f} Gbp/s | "
       f"finalize {t_fin[0]:.3f} ms | K2 {t_k2[0]:.3f} ms = {n*(n-1)/2/t_k2[0]/1e3:.2f} Mpairs/s | "
       f"sum(counts)={chk} sum(ov)={int(ov.to(torch.int64).sum().item())}")
