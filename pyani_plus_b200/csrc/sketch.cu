@@ -112,13 +112,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int K>
 __global__ void __launch_bounds__(kThreadsK1, PANIB_K1_MINBLOCKS)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
-                   const int64_t *__restrict__ tile_off, int n_genomes, int64_t n_tiles, uint32_t seed,
-                   uint64_t max_hash, const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
-                   uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
-    // CTA-sized tiles (variant 0): persistent CTAs, double buffer, two barriers per tile
+                   const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
+                   uint32_t seed, uint64_t max_hash, const int32_t *__restrict__ nb,
+                   const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
+                   int32_t *flags, int32_t *status) {
+    // tiles [tile_begin, n_tiles): persistent CTAs, double buffer, two barriers per tile
     __shared__ __align__(16) uint32_t sp[2][kTileWords];
     __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
-    int64_t tile = blockIdx.x;
+    int64_t tile = tile_begin + blockIdx.x;
     if (tile >= n_tiles) return;
     auto prefetch = [&](int64_t t, int b) {
         const uint32_t *gp = packed + t * (kTileBases / 16);
@@ -181,13 +182,14 @@ __device__ __forceinline__ uint32_t base_at(const uint32_t *sp, int pos) {
 
 __global__ void __launch_bounds__(256)
 sketch_hash_generic_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
-                           const int64_t *__restrict__ tile_off, int n_genomes, int64_t n_tiles, int k,
-                           uint32_t seed, uint64_t max_hash, const int32_t *__restrict__ nb,
+                           const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin,
+                           int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                           const int32_t *__restrict__ nb,
                            const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
                            int32_t *flags, int32_t *status) {
     __shared__ uint32_t sp[kGenWords];
     __shared__ uint32_t sm[kGenMask];
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+    const int64_t tile = tile_begin + (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
     if (tile >= n_tiles) return;
     stage_tile<kGenWords, kGenMask>(packed, mask, tile, sp, sm);
     const int g = find_genome(tile_off, n_genomes, tile, 0);
@@ -327,37 +329,53 @@ extern "C" int panib_pack_ascii(const uint8_t *d_ascii, int64_t n_bases, uint32_
     return check_launch("pack_ascii_kernel");
 }
 
-extern "C" int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
-                                      int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
-                                      const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
-                                      int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream) {
-    if (k < 1 || k > PANIB_MAX_K) {
-        set_error("k-mer size %d outside 1..%d", k, PANIB_MAX_K);
-        return PANIB_E_ARG;
-    }
-    if (n_genomes <= 0 || n_tiles <= 0) return PANIB_OK;
-    if (row_stride <= 0 || row_stride % kBucketSlots) {
-        set_error("row_stride=%lld must be a positive multiple of %d", (long long)row_stride, kBucketSlots);
-        return PANIB_E_ARG;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    PANIB_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
-    PANIB_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
+// launch K1 over tiles [tile_begin, tile_end) of the stream (table / flags already initialised)
+static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
+                             int64_t n_genomes, int64_t tile_begin, int64_t tile_end, int k, uint32_t seed,
+                             uint64_t max_hash, const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                             int64_t row_stride, int32_t *d_flags, int32_t *d_status, cudaStream_t st) {
+    const int64_t n = tile_end - tile_begin;
+    if (n <= 0) return PANIB_OK;
 #define PANIB_LAUNCH_K(KK)                                                                                   \
-    sketch_hash_kernel<KK><<<persistent_grid<KK>(n_tiles), kThreadsK1, 0, st>>>(                              \
-        d_packed, d_mask, d_tile_off, (int)n_genomes, n_tiles, seed, max_hash, d_nb, d_bmul, d_table,        \
-        row_stride, d_flags, d_status)
+    sketch_hash_kernel<KK><<<persistent_grid<KK>(n), kThreadsK1, 0, st>>>(                                    \
+        d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, seed, max_hash, d_nb, d_bmul,    \
+        d_table, row_stride, d_flags, d_status)
     switch (k) {
     case 21: PANIB_LAUNCH_K(21); break;
     case 31: PANIB_LAUNCH_K(31); break;
     default:
-        sketch_hash_generic_kernel<<<tile_grid(n_tiles), 256, 0, st>>>(d_packed, d_mask, d_tile_off,
-                                                                        (int)n_genomes, n_tiles, k, seed, max_hash,
-                                                                        d_nb, d_bmul, d_table, row_stride, d_flags,
-                                                                        d_status);
+        sketch_hash_generic_kernel<<<tile_grid(n), 256, 0, st>>>(d_packed, d_mask, d_tile_off, (int)n_genomes,
+                                                                  tile_begin, tile_end, k, seed, max_hash, d_nb,
+                                                                  d_bmul, d_table, row_stride, d_flags, d_status);
     }
 #undef PANIB_LAUNCH_K
     return check_launch("sketch_hash_kernel");
+}
+
+static int check_sketch_args(int k, int64_t row_stride) {
+    if (k < 1 || k > PANIB_MAX_K) {
+        set_error("k-mer size %d outside 1..%d", k, PANIB_MAX_K);
+        return PANIB_E_ARG;
+    }
+    if (row_stride <= 0 || row_stride % kBucketSlots) {
+        set_error("row_stride=%lld must be a positive multiple of %d", (long long)row_stride, kBucketSlots);
+        return PANIB_E_ARG;
+    }
+    return PANIB_OK;
+}
+
+extern "C" int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
+                                      int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                                      const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                                      int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream) {
+    int rc = check_sketch_args(k, row_stride);
+    if (rc) return rc;
+    if (n_genomes <= 0 || n_tiles <= 0) return PANIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PANIB_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
+    PANIB_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
+    return launch_hash_range(d_packed, d_mask, d_tile_off, n_genomes, 0, n_tiles, k, seed, max_hash, d_nb, d_bmul,
+                             d_table, row_stride, d_flags, d_status, st);
 }
 
 extern "C" int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int64_t n_genomes, const int32_t *d_nb,
@@ -379,6 +397,10 @@ extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_m
     return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, stream);
 }
 
+// Host-buffer form.  The stream is cut into chunks; chunk c+1 is copied host->device on an internal
+// copy stream while chunk c is packed and hashed on the caller's stream, so that the PCIe transfer
+// (1 byte per base) and K1 overlap.  K1 of a chunk stops one tile short of the chunk's end, because
+// the last tile's k-1 halo lives in the next chunk; that tile is hashed with the next chunk.
 extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
                                        uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
                                        int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
@@ -389,9 +411,53 @@ extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii,
         set_error("n_bases=%lld must equal (n_tiles+1)*%d", (long long)n_bases, kTileBases);
         return PANIB_E_ARG;
     }
-    PANIB_CUDA(cudaMemcpyAsync(d_ascii, h_ascii, (size_t)n_bases, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    int rc = panib_pack_ascii(d_ascii, n_bases, d_packed, d_mask, stream);
+    int rc = check_sketch_args(k, row_stride);
     if (rc) return rc;
-    return panib_sketch_stream(d_packed, d_mask, d_tile_off, n_genomes, n_tiles, k, seed, max_hash, d_nb, d_bmul,
-                               d_table, row_stride, d_counts, d_flags, d_status, stream);
+    if (n_genomes <= 0 || n_tiles <= 0) return PANIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    constexpr int kMaxChunks = 32;
+    static thread_local cudaStream_t copy_stream = nullptr;
+    static thread_local cudaEvent_t ev_copied[kMaxChunks], ev_ready = nullptr;
+    static thread_local int ev_device = -1;
+    int dev = 0;
+    PANIB_CUDA(cudaGetDevice(&dev));
+    if (!copy_stream || ev_device != dev) {
+        PANIB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; i++)
+            PANIB_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+        PANIB_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+        ev_device = dev;
+    }
+    // chunks of whole tiles, >= 4 MiB each, at most kMaxChunks; the trailing pad tile rides with the last
+    const int64_t total_tiles = n_tiles + 1;
+    int64_t per = (total_tiles + kMaxChunks - 1) / kMaxChunks;
+    if (per < 1024) per = 1024;
+    const int n_chunks = (int)((total_tiles + per - 1) / per);
+
+    PANIB_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
+    PANIB_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
+    // the copy stream must not overwrite d_ascii while earlier work on `st` may still read it
+    PANIB_CUDA(cudaEventRecord(ev_ready, st));
+    PANIB_CUDA(cudaStreamWaitEvent(copy_stream, ev_ready, 0));
+    for (int c = 0; c < n_chunks; c++) {
+        const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles;
+        PANIB_CUDA(cudaMemcpyAsync(d_ascii + t0 * kTileBases, h_ascii + t0 * kTileBases,
+                                   (size_t)(t1 - t0) * kTileBases, cudaMemcpyHostToDevice, copy_stream));
+        PANIB_CUDA(cudaEventRecord(ev_copied[c], copy_stream));
+    }
+    int64_t hashed = 0;  // tiles [0, hashed) are done
+    for (int c = 0; c < n_chunks; c++) {
+        const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles;
+        PANIB_CUDA(cudaStreamWaitEvent(st, ev_copied[c], 0));
+        rc = panib_pack_ascii(d_ascii + t0 * kTileBases, (t1 - t0) * kTileBases, d_packed + t0 * (kTileBases / 16),
+                              d_mask + t0 * (kTileBases / 32), stream);
+        if (rc) return rc;
+        const int64_t upto = c == n_chunks - 1 ? n_tiles : t1 - 1;  // halo of tile t1-1 is in the next chunk
+        rc = launch_hash_range(d_packed, d_mask, d_tile_off, n_genomes, hashed, upto, k, seed, max_hash, d_nb,
+                               d_bmul, d_table, row_stride, d_flags, d_status, st);
+        if (rc) return rc;
+        if (upto > hashed) hashed = upto;
+    }
+    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, stream);
 }
