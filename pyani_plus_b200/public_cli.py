@@ -1,0 +1,358 @@
+"""Public command line interface: ``pyani-plus sourmash`` and ``pyani-plus resume`` on a B200.
+
+Drop-in for the sourmash path of ``pyani_plus/public_cli.py``: ``cli_sourmash`` (:598-639),
+``start_and_run_method`` (:115-203), ``run_method`` (:206-329) and ``resume`` (:702-828) keep their
+options, log messages, database side effects and error texts.  The reference hands the compute step
+to snakemake, which for sourmash schedules ONE job (``column_0``, :232-235) that runs
+``.pyani-plus-private-cli compute-column --subject 0``; here that one job is run in-process through
+the same ``private_cli.compute_column`` entry point and the same JSON hand-over, so no workflow
+engine is needed.  Only the ``local`` executor exists.
+"""
+
+from __future__ import annotations
+
+import logging
+import sys
+import tempfile
+from contextlib import nullcontext
+from enum import Enum
+from pathlib import Path
+from typing import Annotated
+
+import typer
+from rich.progress import Progress
+
+from pyani_plus_b200 import LOG_FILE, LOG_FILE_DYNAMIC, __version__, db_orm, log_sys_exit, private_cli, setup_logger, tools
+from pyani_plus_b200.db_orm import Session
+from pyani_plus_b200.methods import sourmash
+from pyani_plus_b200.utils import check_db, check_fasta, file_md5sum
+
+app = typer.Typer(no_args_is_help=True, context_settings={"help_option_names": ["-h", "--help"]})
+
+
+class ToolExecutor(str, Enum):
+    """How the compute step is run (the reference also offers slurm through snakemake)."""
+
+    local = "local"
+    slurm = "slurm"
+
+
+REQ_FASTA_DIR = Annotated[Path, typer.Argument(help="Directory of FASTA files (extensions .fas, .fasta, .fna, .fa; "
+                                               "optionally gzipped).", show_default=False)]
+REQ_DB = Annotated[Path, typer.Option("--database", "-d", help="Path to pyANI-plus SQLite3 database.",
+                                      show_default=False, dir_okay=False, file_okay=True)]
+OPT_RUN_NAME = Annotated[str | None, typer.Option(help="Run name. Default is 'N genomes using METHOD'.")]
+OPT_CREATE_DB = Annotated[bool, typer.Option(help="Create database if does not exist.")]
+OPT_EXECUTOR = Annotated[ToolExecutor, typer.Option(help="How should the internal tools be run?")]
+OPT_CACHE = Annotated[Path, typer.Option(help="Cache location for sourmash signatures.", file_okay=False)]
+OPT_TEMP = Annotated[Path | None, typer.Option(help="Directory to use for intermediate files (kept, for debugging).",
+                                               file_okay=False)]
+OPT_WTEMP = Annotated[Path | None, typer.Option(help="Directory to use for the JSON hand-over files.",
+                                                file_okay=False)]
+OPT_LOG = Annotated[Path, typer.Option(help="Where to record log(s). Use '-' for no logging.", dir_okay=False)]
+OPT_SCALED = Annotated[int, typer.Option(help="Sets the compression ratio (FracMinHash scaled).", min=1,
+                                         rich_help_panel="Method parameters")]
+OPT_KMERSIZE = Annotated[int, typer.Option(help="Comparison method k-mer size.", min=1,
+                                           rich_help_panel="Method parameters")]
+OPT_DEBUG = Annotated[bool, typer.Option(help="Show debugging level logging at the terminal.")]
+OPT_RUN_ID = Annotated[int | None, typer.Option("--run-id", "-r", help="Which run from the database "
+                                                "(defaults to latest).", show_default=False)]
+
+
+def version_callback(value: bool) -> None:  # noqa: FBT001
+    if value:
+        print(f"pyANI-plus (B200 sourmash engine) {__version__}")  # noqa: T201
+        raise typer.Exit
+
+
+@app.callback()
+def common(
+    version: Annotated[bool, typer.Option("--version", "-v", help="Show tool version (on stdout) and quit.",
+                                          callback=version_callback, is_eager=True)] = False,  # noqa: FBT002
+) -> None:
+    """pyANI-plus ANI analysis: the sourmash method, computed on an NVIDIA B200."""
+
+
+def start_and_run_method(  # noqa: PLR0913, PLR0917
+    logger: logging.Logger,
+    executor: ToolExecutor,
+    cache: Path,
+    temp: Path | None,
+    workflow_temp: Path | None,
+    database: Path,
+    log: Path,
+    name: str | None,
+    method: str,
+    fasta: Path,
+    tool: tools.ExternalToolData | None,
+    *,
+    fragsize: int | None = None,
+    mode: str | None = None,
+    kmersize: int | None = None,
+    minmatch: float | None = None,
+    extra: str | None = None,
+) -> int:
+    """Record configuration, genomes and a new run in the database, then compute it."""
+    fasta_names = check_fasta(logger, fasta)
+    with db_orm.connect_to_db(logger, database) as session:
+        config = db_orm.db_configuration(
+            session, method, "" if tool is None else tool.exe_path.stem, "" if tool is None else tool.version,
+            fragsize, mode, kmersize, minmatch, extra, create=True,
+        )
+        n = len(fasta_names)
+        filename_to_md5: dict[Path, str] = {}
+        hashes: set[str] = set()
+        with Progress() as progress:
+            for filename in progress.track(fasta_names, description="Indexing FASTAs"):
+                try:
+                    md5 = file_md5sum(filename)
+                except ValueError as err:
+                    log_sys_exit(logger, str(err))
+                filename_to_md5[filename] = md5
+                if md5 in hashes:
+                    dups = "\n" + "\n".join(sorted({str(k) for k, v in filename_to_md5.items() if v == md5}))
+                    msg = f"Multiple genomes with same MD5 checksum {md5}:{dups}"
+                    log_sys_exit(logger, msg)
+                hashes.add(md5)
+                db_orm.db_genome(logger, session, filename, md5, create=True)
+        run = db_orm.add_run(
+            session, config, cmdline=" ".join(sys.argv), fasta_directory=fasta, status="Initialising",
+            name=f"{len(filename_to_md5)} genomes using {method}" if name is None else name, date=None,
+            fasta_to_hash=filename_to_md5,
+        )
+        session.commit()
+        msg = f"{method} run setup with {n} genomes in database"
+        logger.info(msg)
+        return run_method(logger, executor, cache, temp, workflow_temp, filename_to_md5, database, log, session, run)
+
+
+def run_method(  # noqa: PLR0913, PLR0917
+    logger: logging.Logger,
+    executor: ToolExecutor,
+    cache: Path,
+    temp: Path | None,
+    workflow_temp: Path | None,
+    filename_to_md5: dict[Path, str],
+    database: Path,
+    log: Path,
+    session: Session,
+    run: db_orm.Run,
+) -> int:
+    """Compute the comparisons the run still lacks and record them in the database."""
+    run_id = run.run_id
+    method = run.configuration.method
+    logger.debug("Counting pre-existing comparisons for this run...")
+    done = run.comparisons().count()
+    n = len(filename_to_md5)
+    if done == n**2:
+        msg = f"Database already has all {n}²={n**2} {method} comparisons"
+        logger.info(msg)
+        return 0
+    msg = f"Database already has {done} of {n}²={n**2} {method} comparisons, {n**2 - done} needed"
+    logger.info(msg)
+    if method != "sourmash":
+        msg = f"Unknown method {method} for run-id {run_id} in {database}"
+        log_sys_exit(logger, msg)
+    if executor != ToolExecutor.local:
+        msg = f"Executor {executor.value} is not available: the B200 sourmash engine runs in-process (local)"
+        log_sys_exit(logger, msg)
+    # sourmash: all the columns at once, a single worker
+    target = f"{method}.run_{run_id}.column_0.json"
+    logger.debug("Using a single worker")
+    run.status = "Running"
+    session.commit()
+
+    private_cli.prepare(logger, run, cache)  # builds the .sig cache on the GPU
+
+    session.close()  # reduce chance of DB locking
+    del run
+    with (
+        nullcontext(workflow_temp.absolute()) if workflow_temp
+        else tempfile.TemporaryDirectory(prefix="pyani-plus_")
+    ) as tmp:
+        out_path = Path(tmp) / "output"
+        out_path.mkdir(parents=True, exist_ok=True)
+        json_path = out_path / target
+        rc = private_cli.run_compute_column(
+            logger, Path(database).absolute(), run_id, "0", json_path,
+            cache=cache.absolute(), temp=temp.absolute() if temp else Path("-"),
+        )
+        if rc:
+            msg = f"compute-column returned {rc} for run-id {run_id}"
+            log_sys_exit(logger, msg)
+        with db_orm.connect_to_db(logger, database) as session2:
+            run = session2.get_run(run_id)
+            if json_path.is_file():
+                private_cli.import_json_comparisons(logger, session2, json_path)
+            done = run.comparisons().count()
+            if done != n**2:
+                msg = f"Only have {done} of {n}²={n**2} {method} comparisons needed"  # pragma: no cover
+                log_sys_exit(logger, msg)  # pragma: no cover
+            run.cache_comparisons()
+            run.status = "Done"
+            session2.commit()
+    msg = f"Completed {method} run-id {run_id} with {n} genomes in database {database}"
+    logger.info(msg)
+    return 0
+
+
+@app.command("sourmash", rich_help_panel="ANI methods")
+def cli_sourmash(  # noqa: PLR0913
+    fasta: REQ_FASTA_DIR,
+    database: REQ_DB,
+    *,
+    name: OPT_RUN_NAME = None,
+    create_db: OPT_CREATE_DB = False,
+    executor: OPT_EXECUTOR = ToolExecutor.local,
+    cache: OPT_CACHE = Path(),
+    temp: OPT_TEMP = None,
+    wtemp: OPT_WTEMP = None,
+    log: OPT_LOG = LOG_FILE_DYNAMIC,
+    scaled: OPT_SCALED = sourmash.SCALED,  # 1000
+    kmersize: OPT_KMERSIZE = sourmash.KMER_SIZE,
+    debug: OPT_DEBUG = False,
+) -> int:
+    """Execute sourmash (FracMinHash max-containment) ANI calculations, logged to a pyANI-plus SQLite3 database."""
+    if log == LOG_FILE_DYNAMIC:
+        log = Path("-") if executor == ToolExecutor.local else LOG_FILE
+    logger = setup_logger(log, terminal_level=logging.DEBUG if debug else logging.INFO)
+    check_db(logger, database, create_db)
+    return start_and_run_method(
+        logger, executor, cache, temp, wtemp, database, log, name, "sourmash", fasta, tools.get_sourmash(),
+        kmersize=kmersize, extra=f"scaled={scaled}",
+    )
+
+
+@app.command()
+def resume(  # noqa: PLR0913
+    database: REQ_DB,
+    *,
+    run_id: OPT_RUN_ID = None,
+    executor: OPT_EXECUTOR = ToolExecutor.local,
+    cache: OPT_CACHE = Path(),
+    temp: OPT_TEMP = None,
+    wtemp: OPT_WTEMP = None,
+    log: OPT_LOG = LOG_FILE_DYNAMIC,
+    debug: OPT_DEBUG = False,
+) -> int:
+    """Resume any (partial) run already logged in the database.
+
+    Missing pairwise comparisons are computed and the run is marked as complete; a complete run is
+    left alone.  Aborts if the engine version differs from the one recorded for the run.
+    """
+    if log == LOG_FILE_DYNAMIC:
+        log = Path("-") if executor == ToolExecutor.local else LOG_FILE
+    logger = setup_logger(log, terminal_level=logging.DEBUG if debug else logging.INFO)
+    if database == ":memory:" or not Path(database).is_file():
+        msg = f"Database {database} does not exist"
+        log_sys_exit(logger, msg)
+    with db_orm.connect_to_db(logger, database) as session:
+        run = db_orm.load_run(session, run_id)
+        if run_id is None:
+            run_id = run.run_id
+            msg = f"Resuming run-id {run_id}"
+            logger.info(msg)
+        config = run.configuration
+        msg = (
+            f"This is a {config.method} run on {run.genomes.count()} genomes, "
+            f"using {config.program} version {config.version}"
+        )
+        logger.info(msg)
+        if not run.genomes.count():
+            msg = f"No genomes recorded for run-id {run_id}, cannot resume."
+            log_sys_exit(logger, msg)
+        if config.method != "sourmash":
+            msg = f"Unknown method {config.method} for run-id {run_id} in {database}"
+            log_sys_exit(logger, msg)
+        tool = tools.get_sourmash()
+        if tool.exe_path.stem != config.program or tool.version != config.version:
+            msg = (
+                f"We have {tool.exe_path.stem} version {tool.version}, but"
+                f" run-id {run_id} used {config.program} version {config.version} instead."
+            )
+            log_sys_exit(logger, msg)
+        fasta = Path(run.fasta_directory)
+        if not fasta.is_dir():
+            msg = f"run-id {run_id} used input folder {fasta}, but that is not a directory (now)."
+            log_sys_exit(logger, msg)
+        filename_to_md5 = {fasta / link.fasta_filename: link.genome_hash for link in run.fasta_hashes}
+        for filename, md5 in filename_to_md5.items():
+            if not filename.is_file():
+                msg = f"run-id {run_id} used {filename} with MD5 {md5} but this FASTA file no longer exists"
+                log_sys_exit(logger, msg)
+        run.status = "Resuming"
+        session.commit()
+        return run_method(logger, executor, cache, temp, wtemp, filename_to_md5, database, log, session, run)
+
+
+@app.command()
+def list_runs(database: REQ_DB) -> int:
+    """List the runs defined in a given pyANI-plus SQLite3 database."""
+    logger = setup_logger(None)
+    if database == ":memory:" or not Path(database).is_file():
+        msg = f"Database {database} does not exist"
+        log_sys_exit(logger, msg)
+    from rich.console import Console  # noqa: PLC0415
+    from rich.table import Table  # noqa: PLC0415
+
+    with db_orm.connect_to_db(logger, database) as session:
+        runs = session.runs()
+        table = Table(title=f"{len(runs)} analysis runs in {database}", row_styles=["dim", ""])
+        for col in ("ID", "Date", "Method", "Done", "Null", "Miss", "Total", "Status", "Name"):
+            table.add_column(col)
+        for run in runs:
+            conf = run.configuration
+            n = run.genomes.count()
+            rows = list(run.comparisons())
+            null = sum(1 for c in rows if c.identity is None)
+            table.add_row(
+                str(run.run_id), str(run.date.date()), conf.method, str(len(rows) - null), str(null),
+                str(n**2 - len(rows)), f"{n**2}={n}²", run.status, run.name,
+            )
+    Console().print(table)
+    return 0
+
+
+@app.command()
+def export_run(  # noqa: PLR0913
+    database: REQ_DB,
+    outdir: Annotated[Path, typer.Option(help="Output directory (created if missing).", file_okay=False,
+                                         show_default=False)],
+    run_id: OPT_RUN_ID = None,
+    label: Annotated[str, typer.Option(help="How to label the genomes: md5, filename or stem.")] = "stem",
+) -> int:
+    """Export the run's matrices (identity, query coverage, hadamard, tANI) and the long-form table as TSV."""
+    logger = setup_logger(None)
+    if database == ":memory:" or not Path(database).is_file():
+        msg = f"Database {database} does not exist"
+        log_sys_exit(logger, msg)
+    outdir.mkdir(parents=True, exist_ok=True)
+    with db_orm.connect_to_db(logger, database) as session:
+        run = db_orm.load_run(session, run_id, check_empty=True)
+        method = run.configuration.method
+        if run.identities is None:
+            run.cache_comparisons()
+            session.commit()
+        for stem, matrix in (("identity", run.identities), ("query_cov", run.cov_query),
+                             ("hadamard", run.hadamard), ("tANI", run.tani)):
+            try:
+                matrix = run.relabelled_matrix(matrix, label)
+            except ValueError as err:
+                log_sys_exit(logger, str(err))
+            matrix.to_csv(outdir / f"{method}_{stem}.tsv", sep="\t")
+        mapping = {a.genome_hash: a.fasta_filename for a in run.fasta_hashes}
+        with (outdir / f"{method}_run_{run.run_id}.tsv").open("w") as handle:
+            handle.write("#Query\tSubject\tIdentity\tQuery-Cov\n")
+            for comp in sorted(run.comparisons(), key=lambda c: (c.query_hash, c.subject_hash)):
+                handle.write(
+                    f"{mapping[comp.query_hash]}\t{mapping[comp.subject_hash]}\t"
+                    f"{'' if comp.identity is None else comp.identity}\t"
+                    f"{'' if comp.cov_query is None else comp.cov_query}\n"
+                )
+    msg = f"Wrote matrices to {outdir}/{method}_*.tsv"
+    logger.info(msg)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(app())  # pragma: no cover
