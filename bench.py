@@ -26,9 +26,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 from pathlib import Path
 
@@ -219,7 +217,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     import torch
     import torch.distributed as dist
 
-    from pyani_plus_b200 import engine
+    from pyani_plus_b200 import engine, multi_gpu
     from pyani_plus_b200 import stream as pstream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,15 +225,17 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = engine.Engine(local_rank)
     dev = eng.device
 
     n, length, k, scaled, desc = WORKLOADS[args.workload]
     n_pairs = n * (n - 1) // 2
-    per_rank = -(-n // world)  # genomes sketched by each rank (last ranks may hold dummies)
-    g0 = rank * per_rank
-    n_local = max(0, min(n, g0 + per_rank) - g0)
+    # genomes sketched by each rank (last ranks may hold empty dummies so that the gather is fixed-size)
+    g0, g1, per_rank = multi_gpu.slice_for_rank(n, rank, world)
+    n_local = g1 - g0
 
     # ---- inputs: this rank's slice of the genomes, generated on the device, then packed (resident)
     # dummy genomes (length 0) pad the slice so that every rank gathers the same shape
@@ -259,11 +259,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     del d_ascii
 
     n_rows = per_rank * world
-    if world > 1:
-        all_rows = torch.empty((n_rows, plan.row_stride), dtype=torch.int64, device=dev)
-        all_counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    expected_max = int(length / scaled * 1.3) + 64  # sizing hint for K2's shared-memory plan
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     result = {}
@@ -274,17 +270,18 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             eng.sketch_ascii_host(h_ascii, plan, bufs, tab, k)
         else:
             eng.sketch_packed(plan, bufs, tab, k)
+        max_count = None
+        if world == 1:  # one read-back: status bits + largest sketch (sizes K2's shared memory)
+            if eng.check_status():
+                raise engine.EngineError("sketch bucket overflow")  # noqa: TRY003, EM101
+            max_count = eng.last_max_count
         if marks is not None:
             marks[0].record()
-        if world > 1:
-            dist.all_gather_into_tensor(all_rows, tab["table"])
-            dist.all_gather_into_tensor(all_counts, tab["counts"])
-            table = engine.SketchTable(all_rows, all_counts, k, scaled)
-        else:
-            table = engine.SketchTable(tab["table"], tab["counts"], k, scaled)
+        all_rows, all_counts = multi_gpu.all_gather_tables(tab["table"], tab["counts"], world)
+        table = engine.SketchTable(all_rows, all_counts, k, scaled)
         if marks is not None:
             marks[1].record()
-        ov = eng.intersect(table, rank=rank, world=world)
+        ov = eng.intersect(table, rank=rank, world=world, max_count=max_count)
         if marks is not None:
             marks[2].record()
         ident, cov = eng.ani_device(ov, table)
@@ -365,7 +362,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     def finalize_only() -> None:
         engine._check(eng.lib.panib_sketch_finalize(tab["table"].data_ptr(), plan.row_stride, plan.n_genomes,  # noqa: SLF001
                                                     plan.d_nb.data_ptr(), tab["counts"].data_ptr(),
-                                                    tab["flags"].data_ptr(), eng._stream()))  # noqa: SLF001
+                                                    tab["flags"].data_ptr(), 0, eng._stream()))  # noqa: SLF001
 
     reps = max(3, min(args.steps, 10))
     k1_hash_ms = time_kernel(hash_only, reps)
@@ -373,7 +370,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     step(False)
     table = result["table"]
     k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world), reps)
-    counts_host = table.counts.cpu().numpy()[:n].astype(np.int64)
+    counts_host = table.counts.cpu().numpy()[multi_gpu.real_rows(n, world)].astype(np.int64)
 
     e2e_t = timed_loop(True, max(2, args.steps // 2), 3)
 

@@ -64,7 +64,10 @@ extern "C" {
 #define PANIB_E_ARG (-2)           /* invalid argument                                             */
 #define PANIB_E_NODEVICE (-3)      /* no CUDA device: this library has no CPU path                  */
 
-/* bits of the device status word written by kernels (d_status, int32, caller zero-initialises) */
+/* d_status is int32[4], zero-initialised by the caller: [0] = PANIB_ST_* bits OR-ed in by kernels,
+ * [1] = largest sketch size seen by the finalize kernel (atomicMax), [2..3] reserved.
+ * The finalize kernel also stores each row's size in the row's LAST slot (row[row_stride-1]), so a
+ * single all-gather of the rows carries the sizes along. */
 #define PANIB_ST_BUCKET_OVERFLOW 1 /* a sketch bucket filled up: re-run with more buckets           */
 #define PANIB_ST_SEGMENT_OVERFLOW 2/* a pairwise segment exceeded seg_cap: re-run with more cells    */
 
@@ -105,7 +108,7 @@ PANIB_API int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d
                            const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
                            int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream);
 PANIB_API int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int64_t n_genomes, const int32_t *d_nb,
-                          int32_t *d_counts, const int32_t *d_flags, void *stream);
+                          int32_t *d_counts, const int32_t *d_flags, int32_t *d_status, void *stream);
 
 /* Host-buffer form (what a caller holding FASTA bytes uses): copies the pinned ASCII stream
  * host->device on `stream`, packs it and sketches it.  d_ascii is device scratch of n_bases bytes,

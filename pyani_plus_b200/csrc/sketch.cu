@@ -247,7 +247,7 @@ sketch_hash_generic_kernel(const uint32_t *__restrict__ packed, const uint32_t *
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sketch_finalize_kernel(uint64_t *__restrict__ table, int64_t row_stride, const int32_t *__restrict__ nb,
-                       int32_t *__restrict__ counts, const int32_t *__restrict__ flags) {
+                       int32_t *__restrict__ counts, const int32_t *__restrict__ flags, int32_t *status) {
     __shared__ uint64_t s[kBucketSlots];
     __shared__ int s_cnt;
     const int g = blockIdx.x, tid = threadIdx.x;
@@ -282,6 +282,11 @@ sketch_finalize_kernel(uint64_t *__restrict__ table, int64_t row_stride, const i
     if (tid == 0) {
         if ((flags[g] & 1) && off < row_stride) row[off++] = kEmpty;  // the all-ones hash (scaled == 1 only)
         counts[g] = off;
+        // the size also rides in the row's last slot (never a hash slot in practice: buckets are sized
+        // at half load), so that ONE all-gather of the rows moves sketches and sizes together
+        if (off < row_stride) row[row_stride - 1] = (uint64_t)off;
+        else if (status) atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);  // a completely full row: re-plan
+        if (status) atomicMax(status + 1, off);  // largest sketch so far: sizes K2's shared memory
     }
 }
 
@@ -379,10 +384,11 @@ extern "C" int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *
 }
 
 extern "C" int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int64_t n_genomes, const int32_t *d_nb,
-                                     int32_t *d_counts, const int32_t *d_flags, void *stream) {
+                                     int32_t *d_counts, const int32_t *d_flags, int32_t *d_status,
+                                     void *stream) {
     if (n_genomes <= 0) return PANIB_OK;
     sketch_finalize_kernel<<<(unsigned)n_genomes, 256, 0, (cudaStream_t)stream>>>(d_table, row_stride, d_nb,
-                                                                                   d_counts, d_flags);
+                                                                                   d_counts, d_flags, d_status);
     return check_launch("sketch_finalize_kernel");
 }
 
@@ -394,7 +400,7 @@ extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_m
     int rc = panib_sketch_hash_only(d_packed, d_mask, d_tile_off, n_genomes, n_tiles, k, seed, max_hash, d_nb,
                                     d_bmul, d_table, row_stride, d_flags, d_status, stream);
     if (rc) return rc;
-    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, stream);
+    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, d_status, stream);
 }
 
 // Host-buffer form.  The stream is cut into chunks; chunk c+1 is copied host->device on an internal
@@ -459,5 +465,5 @@ extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii,
         if (rc) return rc;
         if (upto > hashed) hashed = upto;
     }
-    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, stream);
+    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, d_status, stream);
 }

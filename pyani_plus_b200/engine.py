@@ -74,7 +74,7 @@ def load_library() -> ctypes.CDLL:
     L.panib_sketch_hash_only.restype = _i32
     L.panib_sketch_hash_only.argtypes = [*sk_args, _vp, _vp, _vp]
     L.panib_sketch_finalize.restype = _i32
-    L.panib_sketch_finalize.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp]
+    L.panib_sketch_finalize.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
     L.panib_sketch_ascii_host.restype = _i32
     L.panib_sketch_ascii_host.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp, _vp]
     L.panib_intersect.restype = _i32
@@ -189,6 +189,7 @@ class Engine:
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.last_max_count = 0
         self.max_batch_bytes = 1 << 31  # ASCII bytes staged per sketch batch
 
     # ------------------------------------------------------------------ helpers
@@ -199,10 +200,12 @@ class Engine:
         return int(self.lib.panib_launch_count())
 
     def _read_status(self) -> int:
-        st = int(self.status[0].item())  # synchronises the stream
-        if st:
+        """One device->host read (synchronises): status bits; remembers the largest sketch size seen."""
+        st, max_count = self.status[:2].tolist()
+        self.last_max_count = int(max_count)
+        if st or max_count:
             self.status.zero_()
-        return st
+        return int(st)
 
     # ------------------------------------------------------------------ stage 0+1: sketch
     def plan_stream(self, tile_off: np.ndarray, scaled: int, slack: float = 1.0) -> "StreamPlan":
@@ -392,6 +395,9 @@ class Engine:
                 1 if symmetric else 0, mh, max_count, cells, seg_cap, idx_buckets,
                 fence.data_ptr(), ov.data_ptr(), ns, rank, world, self.status.data_ptr(), self._stream()))
             st = self._read_status()
+            if st & ST_BUCKET_OVERFLOW:
+                msg = "a sketch bucket overflowed in an earlier sketch call whose status was not checked"
+                raise EngineError(msg)
             if st & ST_SEGMENT_OVERFLOW:
                 cells = max(2, cells * 2) if cells else max(2, 2 * -(-max_count // 4096))
                 if cells > 1 << 16:

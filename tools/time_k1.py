@@ -41,7 +41,7 @@ def timeit(fn):
 t_hash = timeit(lambda: engine._check(eng.lib.panib_sketch_hash_only(*hash_args)))
 t_fin = timeit(lambda: engine._check(eng.lib.panib_sketch_finalize(
     tab["table"].data_ptr(), plan.row_stride, plan.n_genomes, plan.d_nb.data_ptr(), tab["counts"].data_ptr(),
-    tab["flags"].data_ptr(), eng._stream())))
+    tab["flags"].data_ptr(), 0, eng._stream())))
 eng.sketch_packed(plan, bufs, tab, k)
 assert eng.check_status() == 0
 table = engine.SketchTable(tab["table"], tab["counts"], k, scaled)
