@@ -33,7 +33,7 @@ struct Collect {
     int64_t cap;
     int64_t n;
     void operator()(uint64_t h) {
-        if (h - 1ull < max_hash) {
+        if (h != 0ull && h <= max_hash) {
             if (n < cap) out[n] = h;
             n++;
         }
@@ -44,9 +44,10 @@ template <int K>
 static int64_t run(const uint32_t *packed, const uint32_t *mask, int64_t t0, int64_t t1, uint32_t seed,
                    uint64_t max_hash, uint64_t *out, int64_t cap) {
     Collect c{max_hash, out, cap, 0};
-    for (int64_t tile = t0; tile < t1; tile++) {
-        const uint32_t *sp = packed + tile * (kTileBases / 16);
-        const uint32_t *sm = mask + tile * (kTileBases / 32);
+    constexpr int S = kTileBases / kCtaTile;  // CTA tiles per stream tile
+    for (int64_t tile = t0 * S; tile < t1 * S; tile++) {
+        const uint32_t *sp = packed + tile * (kCtaTile / 16);
+        const uint32_t *sm = mask + tile * (kCtaTile / 32);
         uint32_t any = 0;
         for (int i = 0; i < kTileMaskWords; i++) any |= sm[i];
         for (int tid = 0; tid < kThreadsK1; tid++) {

@@ -6,9 +6,9 @@
 // The code is __host__ __device__ so that tests can run the identical logic on the CPU
 // (csrc/hostemu.cpp) and compare it with the oracle before any GPU time is spent.
 //
-// Thread geometry ("stride-4" scheme).  A tile is 4096 k-mer start positions handled by 256 threads.
-// Thread (u = tid>>2, a = tid&3) owns the 16 k-mers starting at tile positions 64u + a + 4j,
-// j = 0..15.  Because the starts are 4 bases = 4 ASCII bytes apart, the ASCII form of the thread's
+// Thread geometry ("stride-4" scheme).  A CTA tile is 256*KPT k-mer start positions handled by 256
+// threads (KPT = kKmersPerThread = 16 in the text below).  Thread (u = tid>>2, a = tid&3) owns the
+// KPT k-mers starting at tile positions 4*KPT*u + a + 4j, j = 0..KPT-1.  Because the starts are 4 bases = 4 ASCII bytes apart, the ASCII form of the thread's
 // SPAN = 60+K bases, expanded ONCE into NA 32-bit registers, contains every one of the 16 k-mers as
 // a register-aligned window G[j .. j+NWD): no per-k-mer byte shifting is needed.  The same holds for
 // the reverse strand: the reverse complement of the whole span, expanded once into H[], contains the
@@ -28,11 +28,16 @@
 
 namespace panib {
 
-constexpr int kTileBases = 4096;     // == PANIB_TILE_BASES
+#ifndef PANIB_KPT
+#define PANIB_KPT 16
+#endif
+constexpr int kTileBases = 4096;     // == PANIB_TILE_BASES: alignment unit of genomes in the base stream
 constexpr int kThreadsK1 = 256;
-constexpr int kKmersPerThread = 16;  // 256 threads * 16 = 4096
-constexpr int kTileWords = kTileBases / 16 + 8;   // packed words staged per tile (tile + halo)
-constexpr int kTileMaskWords = kTileBases / 32 + 4;
+constexpr int kKmersPerThread = PANIB_KPT;                  // k-mers per thread (multiple of 4)
+constexpr int kCtaTile = kThreadsK1 * kKmersPerThread;      // k-mer starts per CTA pass (divides kTileBases)
+constexpr int kTileWords = kCtaTile / 16 + 8;               // packed words staged per CTA tile (tile + halo)
+constexpr int kTileMaskWords = kCtaTile / 32 + 4;
+static_assert(kKmersPerThread % 4 == 0 && kTileBases % kCtaTile == 0, "tile geometry");
 
 // ---- small intrinsics with host emulation ---------------------------------------------------
 PANIB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
@@ -83,6 +88,12 @@ PANIB_HD uint64_t fmix64(uint64_t k) {
 struct U64 {
     uint32_t lo, hi;
 };
+
+#if defined(__CUDACC__)
+// Multipliers the compiler cannot fold (a __constant__ can be changed by the host): x * kOpq[0] is an
+// IMAD on the FMA pipe where `x * 1` would be folded back into an ALU-pipe add / shift.
+__constant__ uint32_t kOpq[2] = {1u, 0x80000000u};
+#endif
 PANIB_HD U64 make_u64(uint32_t lo, uint32_t hi) { return U64{lo, hi}; }
 PANIB_HD uint64_t to_u64(U64 x) { return ((uint64_t)x.hi << 32) | x.lo; }
 
@@ -137,9 +148,10 @@ PANIB_HD U64 add64(U64 a, U64 b) {
 #if defined(__CUDA_ARCH__) && defined(PANIB_ADD_FMA)
     // 64-bit add as IMAD.WIDE (a.lo * 1 + b) + IMAD (a.hi * 1 + carry-in high word): FMA pipe, not ALU pipe
     uint32_t plo, phi, rhi;
-    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 q, {%3, %4};\n\tmad.wide.u32 p, %2, 1, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
-        : "=r"(plo), "=r"(phi) : "r"(a.lo), "r"(b.lo), "r"(b.hi));
-    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(rhi) : "r"(a.hi), "r"(phi));
+    const uint32_t one = kOpq[0];
+    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 q, {%3, %4};\n\tmad.wide.u32 p, %2, %5, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=r"(plo), "=r"(phi) : "r"(a.lo), "r"(b.lo), "r"(b.hi), "r"(one));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(rhi) : "r"(a.hi), "r"(one), "r"(phi));
     return U64{plo, rhi};
 #else
     const uint64_t r = to_u64(a) + to_u64(b);
@@ -151,8 +163,8 @@ PANIB_HD U64 xorshift33(U64 x) {  // x ^= x >> 33
 #if defined(__CUDA_ARCH__) && defined(PANIB_XS_WIDE)
     // hi >> 1 as the upper half of hi * 2^31 (IMAD.WIDE on the FMA pipe instead of SHF on the ALU pipe)
     uint32_t s, dummy;
-    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, 0x80000000;\n\tmov.b64 {%0, %1}, p;\n\t}"
-        : "=r"(dummy), "=r"(s) : "r"(x.hi));
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=r"(dummy), "=r"(s) : "r"(x.hi), "r"(kOpq[1]));
     return U64{x.lo ^ s, x.hi};
 #else
     return U64{x.lo ^ (x.hi >> 1), x.hi};
@@ -273,7 +285,7 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, i
                                 Emit &&emit) {
     using G_ = Geom<K>;
     constexpr int NX = G_::NX, NA = G_::NA, NWD = G_::NWD;
-    const uint32_t *src = sp + 4 * u;  // span starts at tile position 64u + a
+    const uint32_t *src = sp + (kKmersPerThread / 4) * u;  // span starts at tile position 4*KPT*u + a
     uint32_t X[NX];
 #pragma unroll
     for (int w = 0; w < NX - 1; w++) X[w] = shf_r(src[w], src[w + 1], 2 * a);
@@ -318,7 +330,7 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, i
         }
         bool valid = true;
         if (DIRTY) {
-            const int pos = 64 * u + a + 4 * j;
+            const int pos = 4 * kKmersPerThread * u + a + 4 * j;
             uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
             if (K < 32) mw &= (1u << (K & 31)) - 1u;
             valid = (mw == 0u);

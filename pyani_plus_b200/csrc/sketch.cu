@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const uint4 *__restrict
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ void table_insert(uint64_t *__restrict__ row, int nb, uint64_t bmul, uint64_t h,
                                              int32_t *flag, int32_t *status) {
+    if (h == 0ull) return;  // sourmash skips hash 0 (tested here, on the rare path only)
     if (h == kEmpty) {  // only reachable when max_hash == 2^64-1 (scaled == 1); kept as a flag
         atomicOr(flag, 1);
         return;
@@ -68,10 +69,8 @@ struct EmitToTable {
     int32_t *flag;
     int32_t *status;
     __device__ __forceinline__ void operator()(uint64_t h) const {
-        // keep iff 0 < h <= max_hash (sourmash skips hash 0; tested on the rare path only)
-        if (h <= max_hash) {
-            if (h != 0ull) table_insert(row, nb, bmul, h, flag, status);
-        }
+        // keep iff 0 < h <= max_hash
+        if (h <= max_hash) table_insert(row, nb, bmul, h, flag, status);
     }
 };
 
@@ -116,14 +115,17 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
                    uint32_t seed, uint64_t max_hash, const int32_t *__restrict__ nb,
                    const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
                    int32_t *flags, int32_t *status) {
-    // tiles [tile_begin, n_tiles): persistent CTAs, double buffer, two barriers per tile
+    // stream tiles [tile_begin, n_tiles) = CTA tiles [tile_begin*S, n_tiles*S), S = kTileBases/kCtaTile:
+    // persistent CTAs, double buffer, two barriers per CTA tile
     __shared__ __align__(16) uint32_t sp[2][kTileWords];
     __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
-    int64_t tile = tile_begin + blockIdx.x;
+    constexpr int S = kTileBases / kCtaTile;
+    n_tiles *= S;
+    int64_t tile = tile_begin * S + blockIdx.x;
     if (tile >= n_tiles) return;
     auto prefetch = [&](int64_t t, int b) {
-        const uint32_t *gp = packed + t * (kTileBases / 16);
-        const uint32_t *gm = mask + t * (kTileBases / 32);
+        const uint32_t *gp = packed + t * (kCtaTile / 16);
+        const uint32_t *gm = mask + t * (kCtaTile / 32);
         const int x = threadIdx.x;
         if (x < kTileWords / 4) cp_async16(sp[b] + 4 * x, gp + 4 * x);
         else if (x < kTileWords / 4 + kTileMaskWords / 4)
@@ -145,7 +147,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         __syncthreads();
         const uint32_t m = threadIdx.x < kTileMaskWords ? sm[cur][threadIdx.x] : 0u;
         const bool dirty = __syncthreads_or(m != 0u) != 0;
-        g = find_genome(tile_off, n_genomes, tile, g);
+        g = find_genome(tile_off, n_genomes, tile / S, g);
         EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g,
                          status};
         if (!dirty) {
@@ -342,7 +344,7 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
     const int64_t n = tile_end - tile_begin;
     if (n <= 0) return PANIB_OK;
 #define PANIB_LAUNCH_K(KK)                                                                                   \
-    sketch_hash_kernel<KK><<<persistent_grid<KK>(n), kThreadsK1, 0, st>>>(                                    \
+    sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, 0, st>>>(                                    \
         d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, seed, max_hash, d_nb, d_bmul,    \
         d_table, row_stride, d_flags, d_status)
     switch (k) {
