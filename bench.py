@@ -244,19 +244,30 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     for i in range(per_rank):
         tile_off[i + 1] = tile_off[i] + (tiles_per if i < n_local else 1)
     plan = eng.plan_stream(tile_off, scaled)
-    d_ascii = torch.full((plan.n_bases,), pstream.PAD, dtype=torch.uint8, device=dev)
-    if n_local:
-        real_bytes = n_local * tiles_per * pstream.TILE
-        gen, _ = eng.synth_ascii_stream(SEED, g0, n_local, length)
-        d_ascii[:real_bytes] = gen[:real_bytes]
-        del gen
-    bufs = eng.alloc_stream_buffers(plan, ascii_too=True)
-    eng.pack(d_ascii, plan, bufs)
+    bufs = eng.alloc_stream_buffers(plan, ascii_too=False)
     tab = eng.alloc_table(plan)
-    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True)
-    h_ascii.copy_(d_ascii)
-    torch.cuda.synchronize()
-    del d_ascii
+    # e2e needs the whole ASCII stream in pinned host memory; skipped (null) for streams > 12 GB
+    do_e2e = plan.n_bases <= (12 << 30) and not args.no_e2e
+    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True) if do_e2e else None
+    batch = 256  # genomes generated + packed per pass, so that the ASCII form is never fully resident
+    for b0 in range(0, per_rank, batch):
+        b1 = min(per_rank, b0 + batch)
+        t0, t1 = int(tile_off[b0]), int(tile_off[b1]) + (1 if b1 == per_rank else 0)  # + the trailing pad tile
+        d_ascii = torch.full(((t1 - t0) * pstream.TILE,), pstream.PAD, dtype=torch.uint8, device=dev)
+        real = max(0, min(b1, n_local) - b0)
+        if real:
+            gen, _ = eng.synth_ascii_stream(SEED, g0 + b0, real, length)
+            d_ascii[: real * tiles_per * pstream.TILE] = gen[: real * tiles_per * pstream.TILE]
+            del gen
+        engine._check(eng.lib.panib_pack_ascii(  # noqa: SLF001
+            d_ascii.data_ptr(), d_ascii.numel(), bufs["packed"].data_ptr() + t0 * pstream.TILE // 4,
+            bufs["mask"].data_ptr() + t0 * pstream.TILE // 8, eng._stream()))  # noqa: SLF001
+        if do_e2e:
+            h_ascii[t0 * pstream.TILE: t1 * pstream.TILE].copy_(d_ascii)
+        torch.cuda.synchronize()
+        del d_ascii
+    if do_e2e:
+        bufs["ascii"] = torch.empty(plan.n_bases, dtype=torch.uint8, device=dev)
 
     n_rows = per_rank * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -372,7 +383,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world), reps)
     counts_host = table.counts.cpu().numpy()[multi_gpu.real_rows(n, world)].astype(np.int64)
 
-    e2e_t = timed_loop(True, max(2, args.steps // 2), 3)
+    e2e_t = timed_loop(True, max(2, args.steps // 2), 3) if do_e2e else None
 
     if rank != 0:
         if world > 1:
@@ -389,7 +400,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     k2_bytes = (8.0 * (n - 1) * tot_cnt + 4.0 * n_pairs) / world
     k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
     value = n_pairs / (dev_t["ms"] * 1e-3)
-    e2e_value = n_pairs / (e2e_t["ms"] * 1e-3)
+    e2e_value = n_pairs / (e2e_t["ms"] * 1e-3) if e2e_t else None
     dominant_is_k1 = dev_t["k1_ms"] >= dev_t["k2_ms"]
     roof_k1 = {"kernel": "sketch_hash_kernel<31> (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peak,
                "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
@@ -419,11 +430,13 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "cpu_baseline": ({k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
         "cpu_baseline_detail": ({"sketch_gbp_s": cpu["sketch_gbp_s"],
                                  "pairs_per_s_intersect": cpu["pairs_per_s_intersect"]} if cpu else None),
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_t["ms"],
-                "h2d_bytes_per_step": int(plan.n_bases) * world,
-                "d2h_bytes_per_step": int(2 * n_rows * n_rows * 8 + n_rows * 4) * world,
-                "stage_ms": {"h2d_pack_k1": e2e_t["k1_ms"], "allgather": e2e_t["gather_ms"],
-                             "k2_intersect": e2e_t["k2_ms"]}},
+        "e2e": ({"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_t["ms"],
+                 "h2d_bytes_per_step": int(plan.n_bases) * world,
+                 "d2h_bytes_per_step": int(2 * n_rows * n_rows * 8 + n_rows * 4) * world,
+                 "stage_ms": {"h2d_pack_k1": e2e_t["k1_ms"], "allgather": e2e_t["gather_ms"],
+                              "k2_intersect": e2e_t["k2_ms"]}} if e2e_t else
+                {"value": None, "unit": UNIT, "skipped": "ASCII stream larger than the 12 GB host staging limit "
+                                                         "of bench.py (or --no-e2e)"}),
         "gpu_launches": dev_t["launches"],
         "clocks": dev_t["clocks"],
         "sketch_sizes": {"mean": float(counts_host.mean()), "max": int(counts_host.max())},
@@ -442,6 +455,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

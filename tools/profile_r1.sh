@@ -1,18 +1,21 @@
 #!/bin/bash
-# Profiling recipe (B200_PROFILING.md) for the config-2 bench step.  Run under gpurun:
+# Profiling recipe (B200_PROFILING.md) for the bench step.  Run under gpurun:
 #   gpurun --timeout 1500 -- 'bash tools/profile_r1.sh r01'
-# Outputs land in gpurun_out/; summaries are copied to profiles/ by tools/summarise_ncu.py.
+# Raw outputs land in gpurun_out/; `python tools/summarise_ncu.py r01` writes the summaries kept in profiles/.
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-# 1) every launch with its device time (cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+# 1) every launch of the default bench command with its device time (cold-cache, serialised: compare shares)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file $OUT/launches_$TAG.csv $CMD > $OUT/launches_$TAG.log 2>&1
-# 2) full capture of the two hot kernels (one launch each, after warm-up)
+# 2) full capture of the two hot kernels at config 2 (one launch each, after warm-up)
 ncu --set full --clock-control none --import-source on -k regex:sketch_hash_kernel -s 3 -c 1 \
     -f -o $OUT/prof_k1_$TAG $CMD > $OUT/prof_k1_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:intersect_kernel -s 3 -c 1 \
     -f -o $OUT/prof_k2_$TAG $CMD > $OUT/prof_k2_$TAG.log 2>&1
-ls -la $OUT
+# 3) K2 where it matters: 1,000 genomes (config 3), 499,500 pairs in one launch
+ncu --set full --clock-control none --import-source on -k regex:intersect_kernel -s 1 -c 1 \
+    -f -o $OUT/prof_k2c3_$TAG python tools/time_k1.py config3 1 > $OUT/prof_k2c3_$TAG.log 2>&1
+ls -la $OUT | grep $TAG

@@ -98,7 +98,9 @@ def main() -> None:
     launches = OUT / f"launches_{tag}.csv"
     if launches.is_file():
         (PROF / f"{tag}_launches.md").write_text(summarise_launches(launches))
-    for kind, title in (("k1", "K1 sketch_hash_kernel"), ("k2", "K2 intersect_kernel")):
+    for kind, title in (("k1", "K1 sketch_hash_kernel (config 2: 100 x 5 Mb)"),
+                        ("k2", "K2 intersect_kernel (config 2: 4,950 pairs)"),
+                        ("k2c3", "K2 intersect_kernel (config 3: 1,000 genomes, 499,500 pairs)")):
         rep = OUT / f"prof_{kind}_{tag}.ncu-rep"
         if rep.is_file():
             (PROF / f"{tag}_{kind}_ncu.md").write_text(summarise_report(rep, title) + "\n")
