@@ -172,11 +172,12 @@ __global__ void __launch_bounds__(kThreadsK2) intersect_kernel(const K2Args a) {
         }
         auto probe = [&](uint64_t x) {
             const uint32_t b = k2_bucket<kCells>(x, base, pre, mul);
-            const uint32_t e = idx[b];
-            const uint32_t lo = e & 0x7FFFu;
-            cnt += (seg[lo] == x) ? 1u : 0u;
-            cnt += (seg[lo + 1] == x) ? 1u : 0u;
-            if (e >= kIdxMany) {  // rare: walk the rest of a crowded bucket
+            const int e = reinterpret_cast<const int16_t *>(idx)[b];  // sign bit = "crowded bucket" flag
+            const uint32_t lo = (uint32_t)e & 0x7FFFu;
+            // a sketch holds distinct hashes, so at most one slot can match: one predicated add
+            const bool found = (seg[lo] == x) | (seg[lo + 1] == x);
+            if (found) ++cnt;
+            if (e < 0) {  // rare: walk the rest of a crowded bucket
                 const uint32_t hi = idx[b + 1] & 0x7FFFu;
                 for (uint32_t q = lo + 2; q < hi; q++) cnt += (seg[q] == x) ? 1u : 0u;
             }
