@@ -244,20 +244,21 @@ sketch_hash_generic_kernel(const uint32_t *__restrict__ packed, const uint32_t *
 }
 
 // ------------------------------------------------------------------------------------------------
-// finalize: per genome, sort every bucket, drop the empty slots and compact the row in place.
-// One CTA per genome; a bucket (1024 slots, 8 KB) is bitonic-sorted in shared memory.
+// finalize, step 1: sort every 1024-slot bucket of every genome in place (one CTA per bucket, bitonic
+// sort in 8 KB of shared memory).  Empties (all-ones) sort to the end; the number of hashes is left
+// in the bucket's LAST slot (a bucket planned at half load is never full; if it is, the overflow bit
+// is raised and the host re-plans).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-sketch_finalize_kernel(uint64_t *__restrict__ table, int64_t row_stride, const int32_t *__restrict__ nb,
-                       int32_t *__restrict__ counts, const int32_t *__restrict__ flags, int32_t *status) {
+sketch_sort_buckets_kernel(uint64_t *__restrict__ table, int64_t row_stride, int n_genomes,
+                           const int32_t *__restrict__ nb, int32_t *status) {
     __shared__ uint64_t s[kBucketSlots];
     __shared__ int s_cnt;
-    const int g = blockIdx.x, tid = threadIdx.x;
-    uint64_t *row = table + (size_t)g * row_stride;
-    const int n = nb[g];
-    int off = 0;
-    for (int b = 0; b < n; b++) {
-        for (int i = tid; i < kBucketSlots; i += 256) s[i] = row[(size_t)b * kBucketSlots + i];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    for (int g = blockIdx.y; g < n_genomes; g += gridDim.y) {
+        if (b >= nb[g]) continue;  // uniform per CTA
+        uint64_t *bucket = table + (size_t)g * row_stride + (size_t)b * kBucketSlots;
+        for (int i = tid; i < kBucketSlots; i += 256) s[i] = bucket[i];
         if (tid == 0) s_cnt = 0;
         __syncthreads();
         for (int k = 2; k <= kBucketSlots; k <<= 1) {
@@ -277,15 +278,45 @@ sketch_finalize_kernel(uint64_t *__restrict__ table, int64_t row_stride, const i
         }
         __syncthreads();
         const int cnt = s_cnt;
-        for (int i = tid; i < cnt; i += 256) row[off + i] = s[i];
+        if (cnt >= kBucketSlots && tid == 0 && status) atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);
+        for (int i = tid; i < kBucketSlots - 1; i += 256) bucket[i] = s[i];
+        if (tid == 0) bucket[kBucketSlots - 1] = (uint64_t)(cnt < kBucketSlots ? cnt : kBucketSlots - 1);
+        __syncthreads();
+    }
+}
+
+// finalize, step 2: one CTA per genome moves the sorted buckets together (in place, left to right),
+// which yields the globally sorted sketch because buckets are value ranges.
+__global__ void __launch_bounds__(256)
+sketch_compact_kernel(uint64_t *__restrict__ table, int64_t row_stride, const int32_t *__restrict__ nb,
+                      int32_t *__restrict__ counts, const int32_t *__restrict__ flags, int32_t *status) {
+    const int g = blockIdx.x, tid = threadIdx.x;
+    uint64_t *row = table + (size_t)g * row_stride;
+    const int n = nb[g];
+    int off = 0;
+    for (int b = 0; b < n; b++) {
+        const uint64_t *bucket = row + (size_t)b * kBucketSlots;
+        const int cnt = (int)bucket[kBucketSlots - 1];
+        uint64_t v[kBucketSlots / 256];
+#pragma unroll
+        for (int r = 0; r < kBucketSlots / 256; r++) {
+            const int i = tid + 256 * r;
+            v[r] = i < cnt ? bucket[i] : 0ull;
+        }
+        __syncthreads();  // everything is read before anything moves (source and target may overlap)
+#pragma unroll
+        for (int r = 0; r < kBucketSlots / 256; r++) {
+            const int i = tid + 256 * r;
+            if (i < cnt) row[off + i] = v[r];
+        }
         off += cnt;
         __syncthreads();
     }
     if (tid == 0) {
         if ((flags[g] & 1) && off < row_stride) row[off++] = kEmpty;  // the all-ones hash (scaled == 1 only)
         counts[g] = off;
-        // the size also rides in the row's last slot (never a hash slot in practice: buckets are sized
-        // at half load), so that ONE all-gather of the rows moves sketches and sizes together
+        // the size also rides in the row's last slot, so that ONE all-gather of the rows moves
+        // sketches and sizes together
         if (off < row_stride) row[row_stride - 1] = (uint64_t)off;
         else if (status) atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);  // a completely full row: re-plan
         if (status) atomicMax(status + 1, off);  // largest sketch so far: sizes K2's shared memory
@@ -389,9 +420,16 @@ extern "C" int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int6
                                      int32_t *d_counts, const int32_t *d_flags, int32_t *d_status,
                                      void *stream) {
     if (n_genomes <= 0) return PANIB_OK;
-    sketch_finalize_kernel<<<(unsigned)n_genomes, 256, 0, (cudaStream_t)stream>>>(d_table, row_stride, d_nb,
-                                                                                   d_counts, d_flags, d_status);
-    return check_launch("sketch_finalize_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned nbmax = (unsigned)(row_stride / kBucketSlots);
+    const unsigned gy = (unsigned)(n_genomes < 65535 ? n_genomes : 65535);
+    sketch_sort_buckets_kernel<<<dim3(nbmax, gy), 256, 0, st>>>(d_table, row_stride, (int)n_genomes, d_nb,
+                                                                 d_status ? d_status : nullptr);
+    int rc = check_launch("sketch_sort_buckets_kernel");
+    if (rc) return rc;
+    sketch_compact_kernel<<<(unsigned)n_genomes, 256, 0, st>>>(d_table, row_stride, d_nb, d_counts, d_flags,
+                                                               d_status);
+    return check_launch("sketch_compact_kernel");
 }
 
 extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
