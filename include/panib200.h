@@ -85,6 +85,14 @@ PANIB_API uint64_t panib_max_hash(uint64_t scaled);
  * multiplier bmul with bucket(h) = mulhi64(h, bmul) (monotone in h, < nb for h <= max_hash). */
 PANIB_API int panib_plan_buckets(int64_t n_kmers, uint64_t scaled, double slack, int32_t *nb, uint64_t *bmul);
 
+/* ---- ingest (host): FASTA text -> base-stream form ------------------------------------------ */
+/* Parses decompressed FASTA text exactly as pyani_plus/utils.py:40-90 (fasta_bytes_iterator) does and
+ * writes the records' sequences back to back with one 'N' between records.  dst may be NULL to only
+ * measure.  Returns the stream-form length, or PANIB_E_ARG.  out4 = n_records, total_bases,
+ * offset and length (in text) of the first record's title. */
+PANIB_API int64_t panib_fasta_to_stream(const uint8_t *text, int64_t n, uint8_t *dst, int64_t dst_cap,
+                                        int64_t *out4);
+
 /* ---- stage 0: ASCII base stream -> packed 2-bit + validity mask --------------------------- */
 /* n_bases must be a multiple of 32.  Upper-cases; any byte other than A,C,G,T is invalid. */
 PANIB_API int panib_pack_ascii(const uint8_t *d_ascii, int64_t n_bases, uint32_t *d_packed, uint32_t *d_mask,

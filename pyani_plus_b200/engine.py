@@ -86,6 +86,8 @@ def load_library() -> ctypes.CDLL:
     L.panib_ani_device.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]
     L.panib_ani_host.restype = _i32
     L.panib_ani_host.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]
+    L.panib_fasta_to_stream.restype = _i64
+    L.panib_fasta_to_stream.argtypes = [ctypes.c_char_p, _i64, _vp, _i64, ctypes.POINTER(_i64)]
     L.panib_synth_ascii.restype = _i32
     L.panib_synth_ascii.argtypes = [_u64, _i64, _i64, _i64, _vp, _vp]
     _lib = L
@@ -114,6 +116,27 @@ def _check(rc: int) -> None:
         load_library().panib_last_error(buf, 512)
         msg = f"libpanib200 error {rc}: {buf.value.decode(errors='replace')}"
         raise EngineError(msg)
+
+
+def fasta_to_stream(text: bytes) -> tuple[np.ndarray, int, int, bytes | None]:
+    """Parse decompressed FASTA text in C (``panib_fasta_to_stream``).
+
+    Returns (stream-form uint8 array: records back to back with one ``N`` between them, number of
+    records, total bases, title of the first record or None).  Same record semantics as
+    ``utils.fasta_bytes_iterator`` / the reference's ``pyani_plus/utils.py:40-90``.
+    """
+    lib = load_library()
+    out4 = (_i64 * 4)()
+    need = int(lib.panib_fasta_to_stream(text, len(text), None, 0, out4))
+    if need < 0:
+        _check(need)
+    stream = np.empty(need, dtype=np.uint8)
+    if need:
+        got = int(lib.panib_fasta_to_stream(text, len(text), stream.ctypes.data, need, out4))
+        if got != need:
+            _check(got if got < 0 else -2)
+    title = text[out4[2]: out4[2] + out4[3]] if out4[2] >= 0 else None
+    return stream, int(out4[0]), int(out4[1]), title
 
 
 def ani_host(ov: np.ndarray, q_counts: np.ndarray, s_counts: np.ndarray, k: int) -> tuple[np.ndarray, np.ndarray]:
@@ -304,14 +327,16 @@ class Engine:
                 continue
             return SketchTable(tab["table"][: plan.n_genomes], tab["counts"][: plan.n_genomes], k, scaled)
 
-    def sketch_genomes(self, genomes: list[list[bytes]], k: int, scaled: int, *, seed: int = 42) -> SketchTable:
-        """Sketch genomes given as lists of record sequences (what a FASTA parser yields).
+    def sketch_genomes(self, genomes: list, k: int, scaled: int, *, seed: int = 42) -> SketchTable:
+        """Sketch genomes given as lists of record sequences (what a FASTA parser yields) or as
+        stream-form uint8 arrays (records already joined by one ``N``, see ``fasta_to_stream``).
 
         Genomes are staged in batches of at most ``max_batch_bytes`` of pinned host memory; the
         per-batch tables are compacted into one table whose stride is the largest sketch size.
         """
         torch = self.torch
-        lengths = [_stream.genome_stream_length(g) for g in genomes]
+        genomes = [g if isinstance(g, np.ndarray) else np.frombuffer(b"N".join(g), dtype=np.uint8) for g in genomes]
+        lengths = [int(g.size) for g in genomes]
         batches: list[tuple[int, int]] = []
         start, acc = 0, 0
         for i, length in enumerate(lengths):
@@ -327,7 +352,7 @@ class Engine:
             tile_off = _stream.plan_tiles(lengths[b0:b1])
             nbytes = _stream.stream_bytes(tile_off)
             h_ascii = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-            _stream.fill_ascii_stream(h_ascii.numpy(), tile_off, genomes[b0:b1])
+            _stream.fill_ascii_stream(h_ascii.numpy(), tile_off, [[g] for g in genomes[b0:b1]])
             parts.append(self.sketch_ascii_stream(h_ascii, tile_off, k, scaled, seed=seed))
         return self.concat_tables(parts, k, scaled)
 

@@ -90,8 +90,10 @@ def prepare_genomes(logger: logging.Logger, run: db_orm.Run, cache: Path) -> Ite
 
     from pyani_plus_b200 import engine  # noqa: PLC0415
 
+    from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
+
     max_hash = engine.max_hash(scaled)
-    pending: list[tuple[db_orm.RunGenomeAssociation, Path, list[bytes]]] = []
+    pending: list[tuple[db_orm.RunGenomeAssociation, Path, np.ndarray]] = []
     pending_bytes = 0
 
     def flush() -> Iterator[db_orm.RunGenomeAssociation]:
@@ -107,17 +109,25 @@ def prepare_genomes(logger: logging.Logger, run: db_orm.Run, cache: Path) -> Ite
             pending.clear()
             pending_bytes = 0
 
+    todo = []
     for entry in run.fasta_hashes:
-        fasta_filename = fasta_dir / entry.fasta_filename
-        sig_filename = cache / f"{entry.genome_hash}.sig"
-        if sig_filename.is_file():
+        if (cache / f"{entry.genome_hash}.sig").is_file():
             yield entry
-            continue
-        records = [seq for _, seq in utils.read_fasta_records(fasta_filename)]
-        pending.append((entry, fasta_filename, records))
-        pending_bytes += sum(len(r) for r in records)
-        if pending_bytes >= PREPARE_BATCH_BYTES:
-            yield from flush()
+        else:
+            todo.append(entry)
+    # gunzip + FASTA parsing (C, GIL released) on a thread pool, in order, a bounded window ahead
+    with ThreadPoolExecutor(max_workers=max(1, min(16, utils.available_cores()))) as pool:
+        window = 4 * pool._max_workers  # noqa: SLF001
+        futures = [pool.submit(utils.read_fasta_stream, fasta_dir / e.fasta_filename) for e in todo[:window]]
+        for i, entry in enumerate(todo):
+            if i + window < len(todo):
+                futures.append(pool.submit(utils.read_fasta_stream, fasta_dir / todo[i + window].fasta_filename))
+            stream_bytes = futures[i].result()[0]
+            futures[i] = None  # type: ignore[call-overload]
+            pending.append((entry, fasta_dir / entry.fasta_filename, stream_bytes))
+            pending_bytes += int(stream_bytes.size)
+            if pending_bytes >= PREPARE_BATCH_BYTES:
+                yield from flush()
     yield from flush()
 
 
@@ -204,32 +214,19 @@ def _ani(containment: float, ksize: int) -> float:
     return 1.0 - (1.0 - containment ** (1.0 / ksize))
 
 
-def compute_sourmash_tile(  # noqa: PLR0913, PLR0917
+def tile_arrays(  # noqa: PLR0913
     logger: logging.Logger,
-    tool: tools.ExternalToolData,  # noqa: ARG001
     subject_hashes: set[str],
     query_hashes: set[str],
     cache: Path,
-    tmp_dir: Path,
-) -> Iterator[tuple[str, str, float | None, float | None]]:
-    """Intersect the cached sketches of queries x subjects on the GPU and return pairwise ANI values.
+    tmp_dir: Path | None,
+) -> tuple[list[str], list[str], np.ndarray, np.ndarray, np.ndarray]:
+    """GPU part of ``compute_sourmash_tile``: (queries, subjects, ov, identity, cov_query) as arrays.
 
-    Yields (query_hash, subject_hash, query-containment ANI, max-containment ANI) for EVERY ordered
-    pair; pairs without a common hash (no manysearch row) carry ``None, None``.
+    ``queries`` / ``subjects`` are the sorted MD5 lists labelling the rows / columns; ``ov`` holds the
+    intersection sizes, ``identity`` / ``cov_query`` the max- and query-containment ANI with NaN
+    where branchwater would print no row.
     """
-    if not cache.is_dir():
-        msg = f"Given cache directory '{cache}' does not exist"
-        raise ValueError(msg)
-    query_sig_list = tmp_dir / "query_sigs.csv"
-    subject_sig_list = tmp_dir / "subject_sigs.csv"
-    manysearch = tmp_dir / "manysearch.csv"
-    for csv, sigs in ((query_sig_list, query_hashes), (subject_sig_list, subject_hashes)):
-        if csv.is_file():
-            msg = f"Race condition? Replacing intermediate file '{csv}'"
-            logger.warning(msg)
-            csv.unlink()
-        csv.write_text("internal_location\n" + "".join(f"{cache / (_ + '.sig')}\n" for _ in sorted(sigs)))
-
     m = re.fullmatch(r"sourmash_k=(\d+)_scaled=(\d+)", cache.name)
     queries, subjects = sorted(query_hashes), sorted(subject_hashes)
     loaded: dict[str, dict] = {}
@@ -240,7 +237,8 @@ def compute_sourmash_tile(  # noqa: PLR0913, PLR0917
             log_sys_exit(logger, msg)
         loaded[md5] = sigfile.read_sig(sig_path, ksize=int(m.group(1)) if m else None)
     if not loaded:
-        return
+        empty = np.zeros((0, 0))
+        return queries, subjects, empty.astype(np.uint32), empty, empty
     ksizes = {s["ksize"] for s in loaded.values()}
     max_hashes = {s["max_hash"] for s in loaded.values()}
     if len(ksizes) != 1 or len(max_hashes) != 1:
@@ -270,21 +268,49 @@ def compute_sourmash_tile(  # noqa: PLR0913, PLR0917
     s_counts = s_table.counts.cpu().numpy()
     # host finalisation with libm pow: the floats are the ones branchwater prints
     identity, cov_query = engine.ani_host(ov, q_counts, s_counts, ksize)
-
-    if len(queries) * len(subjects) <= MANYSEARCH_CSV_MAX_ROWS:
+    if tmp_dir is not None and len(queries) * len(subjects) <= MANYSEARCH_CSV_MAX_ROWS:
         write_manysearch_csv(
-            manysearch, queries, subjects, [loaded[h]["md5sum"] for h in queries],
+            tmp_dir / "manysearch.csv", queries, subjects, [loaded[h]["md5sum"] for h in queries],
             [loaded[h]["md5sum"] for h in subjects], q_counts, s_counts, ov, ksize, scaled,
         )
+    for i in np.flatnonzero([q in subject_hashes for q in queries]):  # self-vs-self must be one
+        j = subjects.index(queries[i])
+        if ov[i, j] and identity[i, j] != 1.0:
+            msg = f"Expected sourmash manysearch {queries[i]} vs self to be one, not {identity[i, j]!r}"
+            raise ValueError(msg)
+    return queries, subjects, ov, identity, cov_query
 
+
+def compute_sourmash_tile(  # noqa: PLR0913, PLR0917
+    logger: logging.Logger,
+    tool: tools.ExternalToolData,  # noqa: ARG001
+    subject_hashes: set[str],
+    query_hashes: set[str],
+    cache: Path,
+    tmp_dir: Path,
+) -> Iterator[tuple[str, str, float | None, float | None]]:
+    """Intersect the cached sketches of queries x subjects on the GPU and return pairwise ANI values.
+
+    Yields (query_hash, subject_hash, query-containment ANI, max-containment ANI) for EVERY ordered
+    pair; pairs without a common hash (no manysearch row) carry ``None, None``.
+    """
+    if not cache.is_dir():
+        msg = f"Given cache directory '{cache}' does not exist"
+        raise ValueError(msg)
+    query_sig_list = tmp_dir / "query_sigs.csv"
+    subject_sig_list = tmp_dir / "subject_sigs.csv"
+    for csv, sigs in ((query_sig_list, query_hashes), (subject_sig_list, subject_hashes)):
+        if csv.is_file():
+            msg = f"Race condition? Replacing intermediate file '{csv}'"
+            logger.warning(msg)
+            csv.unlink()
+        csv.write_text("internal_location\n" + "".join(f"{cache / (_ + '.sig')}\n" for _ in sorted(sigs)))
+    queries, subjects, ov, identity, cov_query = tile_arrays(logger, subject_hashes, query_hashes, cache, tmp_dir)
     missing: list[tuple[str, str]] = []
     for i, q in enumerate(queries):
         id_row, cov_row, ov_row = identity[i], cov_query[i], ov[i]
         for j, s in enumerate(subjects):
             if ov_row[j]:
-                if q == s and id_row[j] != 1.0:
-                    msg = f"Expected sourmash manysearch {q} vs self to be one, not {id_row[j]!r}"
-                    raise ValueError(msg)
                 yield q, s, float(cov_row[j]), float(id_row[j])
             else:
                 missing.append((q, s))

@@ -591,5 +591,32 @@ def compute_sourmash(  # noqa: PLR0913, PLR0917
     return 0
 
 
+def compute_sourmash_bulk(logger: logging.Logger, session: Session, run: db_orm.Run, cache: Path) -> int:
+    """All-vs-all for the whole run, recorded straight from arrays (no per-pair dict, no JSON).
+
+    Same row semantics as ``compute_sourmash`` + ``import_json_comparisons`` (N^2 ordered rows,
+    identity := max-containment ANI, cov_query := query-containment ANI, NULL where there is no common
+    hash, INSERT OR IGNORE), for runs too large for the dict / JSON hand-over.
+    Returns the number of ordered pairs computed.
+    """
+    configuration = run.configuration
+    tool = tools.get_sourmash()
+    _check_tool_version(logger, tool, configuration)
+
+    from pyani_plus_b200.methods import sourmash  # noqa: PLC0415
+
+    sig_cache = cache / f"sourmash_k={configuration.kmersize}_{configuration.extra}"
+    if not sig_cache.is_dir():
+        msg = f"Missing sourmash signatures directory '{sig_cache}' - check cache setting '{cache}'."
+        log_sys_exit(logger, msg)
+    hashes = {_.genome_hash for _ in run.fasta_hashes}
+    queries, subjects, _, identity, cov_query = sourmash.tile_arrays(logger, hashes, hashes, sig_cache, None)
+    if not db_orm.insert_comparison_arrays(logger, session, configuration.configuration_id, queries, subjects,
+                                           identity, cov_query):
+        msg = "Failed to record comparisons to database"  # pragma: no cover
+        log_sys_exit(logger, msg)  # pragma: no cover
+    return len(queries) * len(subjects)
+
+
 if __name__ == "__main__":
     sys.exit(app())  # pragma: no cover

@@ -29,6 +29,10 @@ from pyani_plus_b200.utils import check_db, check_fasta, file_md5sum
 
 app = typer.Typer(no_args_is_help=True, context_settings={"help_option_names": ["-h", "--help"]})
 
+# Runs with more genomes than this record their comparisons straight from arrays
+# (private_cli.compute_sourmash_bulk) instead of through the per-pair dict + JSON hand-over.
+BULK_THRESHOLD = 200
+
 
 class ToolExecutor(str, Enum):
     """How the compute step is run (the reference also offers slurm through snakemake)."""
@@ -163,6 +167,20 @@ def run_method(  # noqa: PLR0913, PLR0917
     session.commit()
 
     private_cli.prepare(logger, run, cache)  # builds the .sig cache on the GPU
+
+    if n > BULK_THRESHOLD:
+        logger.debug("Recording comparisons from arrays (bulk path)")
+        private_cli.compute_sourmash_bulk(logger, session, run, cache)
+        done = run.comparisons().count()
+        if done != n**2:
+            msg = f"Only have {done} of {n}²={n**2} {method} comparisons needed"  # pragma: no cover
+            log_sys_exit(logger, msg)  # pragma: no cover
+        run.cache_comparisons()
+        run.status = "Done"
+        session.commit()
+        msg = f"Completed {method} run-id {run_id} with {n} genomes in database {database}"
+        logger.info(msg)
+        return 0
 
     session.close()  # reduce chance of DB locking
     del run

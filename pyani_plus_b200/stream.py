@@ -48,5 +48,5 @@ def fill_ascii_stream(buf: np.ndarray, tile_off: np.ndarray, genomes: list[list[
                 pos += 1  # separator stays invalid
             n = len(rec)
             if n:
-                buf[pos: pos + n] = np.frombuffer(rec, dtype=np.uint8)
+                buf[pos: pos + n] = rec if isinstance(rec, np.ndarray) else np.frombuffer(rec, dtype=np.uint8)
             pos += n

@@ -63,6 +63,21 @@ def read_fasta_records(filename: Path | str) -> list[tuple[bytes, bytes]]:
         return list(fasta_bytes_iterator(handle))
 
 
+def read_fasta_stream(filename: Path | str):  # noqa: ANN201
+    """Read a plain or gzipped FASTA file into base-stream form with the C parser of libpanib200.
+
+    Returns ``(stream uint8 array, n_records, total_bases, first title or None)``; the records are
+    the ones ``fasta_bytes_iterator`` yields, joined by one invalid ``N``.  zlib, the C parser and
+    ctypes all release the GIL, so files can be read by a thread pool.
+    """
+    from pyani_plus_b200 import engine  # noqa: PLC0415
+
+    raw = Path(filename).read_bytes()
+    if raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
+    return engine.fasta_to_stream(raw)
+
+
 def filename_stem(filename: str) -> str:
     """Basename without the FASTA extension, also dropping a ``.gz`` suffix.
 

@@ -314,3 +314,27 @@ def test_synthetic_100_genome_run_matches_engine(tmp_path: Path) -> None:
             else:
                 assert c.identity == ident[i, j] and c.cov_query == cov[i, j]
         assert nulls > 0  # distant synthetic genomes share no hash: the NULL path is exercised
+
+
+def test_bulk_result_path_equals_json_path(tmp_path: Path, input_genomes_tiny: Path, monkeypatch) -> None:
+    """The array-backed recording used for large runs writes the same rows as the JSON hand-over,
+    including INSERT OR IGNORE on resume of a partial run."""
+    db_json, db_bulk = tmp_path / "json.db", tmp_path / "bulk.db"
+    assert public_cli.cli_sourmash(database=db_json, fasta=input_genomes_tiny, scaled=300, create_db=True,
+                                   cache=tmp_path) == 0
+    monkeypatch.setattr(public_cli, "BULK_THRESHOLD", 0)
+    assert public_cli.cli_sourmash(database=db_bulk, fasta=input_genomes_tiny, scaled=300, create_db=True,
+                                   cache=tmp_path) == 0
+    logger = setup_logger(None)
+    rows = {}
+    for db in (db_json, db_bulk):
+        with db_orm.connect_to_db(logger, db) as session:
+            (run,) = session.runs()
+            assert run.status == "Done"
+            rows[db] = sorted((c.query_hash, c.subject_hash, c.identity, c.cov_query, c.aln_length, c.sim_errors,
+                               c.cov_subject, c.uname_machine) for c in run.comparisons())
+            mats = (run.df_identity, run.df_cov_query, run.df_hadamard)
+            rows[str(db)] = mats
+    assert rows[db_json] == rows[db_bulk] and len(rows[db_bulk]) == 9
+    assert rows[str(db_json)] == rows[str(db_bulk)]
+    compare_db_matrices(db_bulk, input_genomes_tiny / "matrices")

@@ -361,3 +361,25 @@ def test_manysearch_number_format() -> None:
     assert sourmash._fmt(0.8888888888888888) == "0.8888888888888888"  # noqa: SLF001
     assert sourmash._fmt(0.00001234) == "0.00001234"  # noqa: SLF001
     assert sourmash._fmt(0.014417744916820702) == "0.014417744916820702"  # noqa: SLF001
+
+
+# ------------------------------------------------------------------------------------- C FASTA ingest
+def test_c_fasta_parser_matches_python_iterator(golden: Path, tmp_path: Path) -> None:
+    """panib_fasta_to_stream == fasta_bytes_iterator records joined by one N (fixtures + mangled input)."""
+    from pyani_plus_b200 import engine
+
+    files = [golden / "viral_example" / "OP073605.fasta", golden / "MIBY01000005.fasta",
+             golden / "bacterial_example" / "NC_002696.fasta.gz", golden / "bacterial_example" / "NC_011916.fas.gz"]
+    messy = tmp_path / "messy.fasta"
+    messy.write_bytes(b"junk\n\n>one desc \t\r\nAC GT\r\n\r\nNN\n>two\n\n>three\nacgt\x0b\n>\nTT")
+    empty = tmp_path / "empty.fasta"
+    empty.write_bytes(b"no records here\nACGT\n")
+    for f in [*files, messy, empty]:
+        records = utils.read_fasta_records(f)
+        stream, n_records, total, title = utils.read_fasta_stream(f)
+        assert n_records == len(records)
+        assert total == sum(len(s) for _, s in records)
+        assert stream.tobytes() == b"N".join(s for _, s in records)
+        assert title == (records[0][0] if records else None)
+    stream, n, total, title = engine.fasta_to_stream(b"")
+    assert (stream.size, n, total, title) == (0, 0, 0, None)
