@@ -17,7 +17,6 @@ is an array-backed bulk insert for large runs.
 from __future__ import annotations
 
 import datetime
-import gzip
 import logging
 import platform
 import sqlite3
@@ -28,7 +27,7 @@ from time import sleep
 from typing import TYPE_CHECKING, Any
 
 from pyani_plus_b200 import log_sys_exit
-from pyani_plus_b200.utils import fasta_bytes_iterator, filename_stem
+from pyani_plus_b200.utils import filename_stem
 
 if TYPE_CHECKING:
     from pandas import DataFrame
@@ -553,42 +552,38 @@ def db_configuration(  # noqa: PLR0913, PLR0917
     return Configuration(row[0], *values)
 
 
-def db_genome(
-    logger: logging.Logger, session: Session, fasta_filename: Path | str, md5: str, *, create: bool = False
+def db_genome(  # noqa: PLR0913
+    logger: logging.Logger, session: Session, fasta_filename: Path | str, md5: str, *, create: bool = False,
+    stats: tuple[int, bytes | None, bool] | None = None,
 ) -> Genome:
-    """Return a genome entry, adding it first if ``create`` and not already there (trusts ``md5``)."""
+    """Return a genome entry, adding it first if ``create`` and not already there (trusts ``md5``).
+
+    ``stats`` = (total bases, first title, file was gzip) when the caller has already scanned the file
+    (``utils.fasta_file_stats``); otherwise the file is scanned here.
+    """
     old = session.get_genome(md5)
     if old is not None:
         return old
     if not create:
         msg = "Requested genome not already in DB"
         raise NoResultFound(msg)
-    length = 0
-    description = None
     name = Path(fasta_filename).name
-    with Path(fasta_filename).open("rb") as probe:
-        is_gzip = probe.read(2) == b"\x1f\x8b"
+    if stats is None:
+        from pyani_plus_b200.utils import fasta_file_stats  # noqa: PLC0415
+
+        stats = fasta_file_stats(fasta_filename)[1:]
+    length, title, is_gzip = stats
+    description = None if title is None else title.decode()
     if is_gzip:
-        with gzip.open(fasta_filename, "rb") as handle:
-            for title, seq in fasta_bytes_iterator(handle):
-                length += len(seq)
-                if description is None:
-                    description = title.decode()
         if description is None:
             msg = f"File {name} is not recognised as a FASTA record"
             log_sys_exit(logger, msg)
         if not str(fasta_filename).endswith(".gz"):
             msg = f"No .gz ending, but {name} is gzip compressed"
             log_sys_exit(logger, msg)
-    else:
-        if str(fasta_filename).endswith(".gz"):
-            msg = f"Has .gz ending, but {name} is NOT gzip compressed"
-            log_sys_exit(logger, msg)
-        with Path(fasta_filename).open("rb") as handle:
-            for title, seq in fasta_bytes_iterator(handle):
-                length += len(seq)
-                if description is None:
-                    description = title.decode()
+    elif str(fasta_filename).endswith(".gz"):
+        msg = f"Has .gz ending, but {name} is NOT gzip compressed"
+        log_sys_exit(logger, msg)
     old = session.get_genome(md5)
     if old is not None:
         return old  # pragma: no cover

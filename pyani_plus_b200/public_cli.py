@@ -25,7 +25,7 @@ from rich.progress import Progress
 from pyani_plus_b200 import LOG_FILE, LOG_FILE_DYNAMIC, __version__, db_orm, log_sys_exit, private_cli, setup_logger, tools
 from pyani_plus_b200.db_orm import Session
 from pyani_plus_b200.methods import sourmash
-from pyani_plus_b200.utils import check_db, check_fasta, file_md5sum
+from pyani_plus_b200.utils import available_cores, check_db, check_fasta, fasta_file_stats
 
 app = typer.Typer(no_args_is_help=True, context_settings={"help_option_names": ["-h", "--help"]})
 
@@ -77,6 +77,14 @@ def common(
     """pyANI-plus ANI analysis: the sourmash method, computed on an NVIDIA B200."""
 
 
+def _scan_fasta(filename: Path):  # noqa: ANN202
+    """Thread-pool worker: ``fasta_file_stats`` with the ValueError returned instead of raised."""
+    try:
+        return fasta_file_stats(filename)
+    except ValueError as err:
+        return err
+
+
 def start_and_run_method(  # noqa: PLR0913, PLR0917
     logger: logging.Logger,
     executor: ToolExecutor,
@@ -106,19 +114,23 @@ def start_and_run_method(  # noqa: PLR0913, PLR0917
         n = len(fasta_names)
         filename_to_md5: dict[Path, str] = {}
         hashes: set[str] = set()
-        with Progress() as progress:
+        from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
+
+        # md5 + length + description from ONE read per file, files in parallel (all GIL-free C)
+        with Progress() as progress, ThreadPoolExecutor(max_workers=max(1, min(16, available_cores()))) as pool:
+            scans = pool.map(_scan_fasta, fasta_names)
             for filename in progress.track(fasta_names, description="Indexing FASTAs"):
-                try:
-                    md5 = file_md5sum(filename)
-                except ValueError as err:
-                    log_sys_exit(logger, str(err))
+                scan = next(scans)
+                if isinstance(scan, ValueError):
+                    log_sys_exit(logger, str(scan))
+                md5, stats = scan[0], scan[1:]
                 filename_to_md5[filename] = md5
                 if md5 in hashes:
                     dups = "\n" + "\n".join(sorted({str(k) for k, v in filename_to_md5.items() if v == md5}))
                     msg = f"Multiple genomes with same MD5 checksum {md5}:{dups}"
                     log_sys_exit(logger, msg)
                 hashes.add(md5)
-                db_orm.db_genome(logger, session, filename, md5, create=True)
+                db_orm.db_genome(logger, session, filename, md5, create=True, stats=stats)
         run = db_orm.add_run(
             session, config, cmdline=" ".join(sys.argv), fasta_directory=fasta, status="Initialising",
             name=f"{len(filename_to_md5)} genomes using {method}" if name is None else name, date=None,

@@ -78,6 +78,33 @@ def read_fasta_stream(filename: Path | str):  # noqa: ANN201
     return engine.fasta_to_stream(raw)
 
 
+def fasta_file_stats(filename: Path | str) -> tuple[str, int, bytes | None, bool]:
+    """One pass over a FASTA file: (md5 of decompressed bytes, total bases, first title, was gzip).
+
+    What ``file_md5sum`` plus the length / description scan of ``db_genome`` compute, from a single
+    read; hashlib, zlib and the C parser release the GIL, so a thread pool scales over files.
+    """
+    from pyani_plus_b200 import engine  # noqa: PLC0415
+
+    fname = Path(filename)
+    try:
+        raw = fname.read_bytes()
+    except FileNotFoundError:
+        msg = f"Input {fname} is a broken symlink" if fname.is_symlink() else f"Input {fname} not found"
+        raise ValueError(msg) from None
+    is_gzip = raw[:2] == b"\x1f\x8b"
+    if is_gzip:
+        raw = gzip.decompress(raw)
+    md5 = hashlib.md5(raw).hexdigest()  # noqa: S324
+    lib = engine.load_library()
+    import ctypes  # noqa: PLC0415
+
+    out4 = (ctypes.c_int64 * 4)()
+    lib.panib_fasta_to_stream(raw, len(raw), None, 0, out4)
+    title = raw[out4[2]: out4[2] + out4[3]] if out4[2] >= 0 else None
+    return md5, int(out4[1]), title, is_gzip
+
+
 def filename_stem(filename: str) -> str:
     """Basename without the FASTA extension, also dropping a ``.gz`` suffix.
 
