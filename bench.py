@@ -270,6 +270,11 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         bufs["ascii"] = torch.empty(plan.n_bases, dtype=torch.uint8, device=dev)
 
     n_rows = per_rank * world
+    size_hint = plan.sketch_size_hint()
+    if world > 1:  # all ranks must agree (genome lengths differ between slices in general)
+        hint_t = torch.tensor([size_hint], dtype=torch.int64, device=dev)
+        dist.all_reduce(hint_t, op=dist.ReduceOp.MAX)
+        size_hint = int(hint_t.item())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -281,11 +286,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             eng.sketch_ascii_host(h_ascii, plan, bufs, tab, k)
         else:
             eng.sketch_packed(plan, bufs, tab, k)
-        max_count = None
-        if world == 1:  # one read-back: status bits + largest sketch (sizes K2's shared memory)
-            if eng.check_status():
-                raise engine.EngineError("sketch bucket overflow")  # noqa: TRY003, EM101
-            max_count = eng.last_max_count
+        # no read-back between the stages: K2's shared memory is sized from the genome lengths (the
+        # kernel verifies it), K1's overflow bit is read together with K2's at the end of the step
+        max_count = size_hint
         if marks is not None:
             marks[0].record()
         all_rows, all_counts = multi_gpu.all_gather_tables(tab["table"], tab["counts"], world)

@@ -274,7 +274,13 @@ K2Plan make_plan(uint64_t max_hash, int64_t max_count, int n_cells, int seg_cap,
         seg_cap = (int)((int64_t)(want + 2 + 63) / 64 * 64);
     }
     if (seg_cap > 32767) seg_cap = 32767;
-    if (idx_buckets <= 0) idx_buckets = 3 * seg_cap;
+    if (idx_buckets <= 0) {
+        // ~3 buckets per element, trimmed (not below 2 per element) when that keeps a third CTA
+        // resident on the SM: 3 x (74.5 KB + 1 KB reserved) fit the 227 KB of shared memory
+        idx_buckets = 3 * seg_cap;
+        const int fit = (76288 - seg_cap * 8) / 2 - 2;
+        if (fit < idx_buckets && fit >= 2 * seg_cap) idx_buckets = fit;
+    }
     p.G = n_cells;
     p.seg_cap = seg_cap;
     p.R = idx_buckets;

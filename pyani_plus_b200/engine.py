@@ -195,6 +195,14 @@ class StreamPlan:
     d_nb: "torch.Tensor"  # noqa: F821, UP037
     d_bmul: "torch.Tensor"  # noqa: F821, UP037
 
+    def sketch_size_hint(self) -> int:
+        """Upper estimate of the largest sketch of this stream: expected survivors of the longest
+        genome + 6 sigma.  Lets K2 size its shared memory without a device->host read; the kernel
+        still verifies it (PANIB_ST_SEGMENT_OVERFLOW -> re-plan)."""
+        tiles = int(np.max(np.diff(self.tile_off))) if self.n_genomes else 1
+        expected = tiles * _stream.TILE / max(1, self.scaled)
+        return int(expected + 6.0 * expected ** 0.5 + 64)
+
 
 class Engine:
     """One engine per process / per GPU (``torch.cuda.current_device()``)."""

@@ -25,15 +25,17 @@ import numpy as np
 def slice_for_rank(n_items: int, rank: int, world: int) -> tuple[int, int, int]:
     """Contiguous slice [begin, end) of ``n_items`` owned by ``rank`` and the padded per-rank count.
 
-    Every rank gets ``per_rank = ceil(n / world)`` slots; trailing ranks may own fewer real items
-    (the rest are empty dummy genomes) so that the all-gather is a plain fixed-size one.
+    Every rank gets ``per_rank = ceil(n / world)`` slots so that the all-gather is a plain fixed-size
+    one; the real items are spread as evenly as possible (the first ``n % world`` ranks own one more
+    than the others) and the unused slots of a rank hold empty dummy genomes.
     """
     if world < 1 or not 0 <= rank < world:
         msg = f"bad rank/world {rank}/{world}"
         raise ValueError(msg)
     per_rank = -(-n_items // world) if n_items else 0
-    begin = min(n_items, rank * per_rank)
-    end = min(n_items, begin + per_rank)
+    base, extra = divmod(n_items, world)
+    begin = rank * base + min(rank, extra)
+    end = begin + base + (1 if rank < extra else 0)
     return begin, end, per_rank
 
 
