@@ -32,7 +32,10 @@ namespace panib {
 #define PANIB_KPT 16
 #endif
 constexpr int kTileBases = 4096;     // == PANIB_TILE_BASES: alignment unit of genomes in the base stream
-constexpr int kThreadsK1 = 256;
+#ifndef PANIB_K1_THREADS
+#define PANIB_K1_THREADS 256
+#endif
+constexpr int kThreadsK1 = PANIB_K1_THREADS;
 constexpr int kKmersPerThread = PANIB_KPT;                  // k-mers per thread (multiple of 4)
 constexpr int kCtaTile = kThreadsK1 * kKmersPerThread;      // k-mer starts per CTA pass (divides kTileBases)
 constexpr int kTileWords = kCtaTile / 16 + 8;               // packed words staged per CTA tile (tile + halo)
