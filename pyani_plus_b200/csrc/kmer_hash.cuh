@@ -92,11 +92,6 @@ struct U64 {
     uint32_t lo, hi;
 };
 
-#if defined(__CUDACC__)
-// Multipliers the compiler cannot fold (a __constant__ can be changed by the host): x * kOpq[0] is an
-// IMAD on the FMA pipe where `x * 1` would be folded back into an ALU-pipe add / shift.
-__constant__ uint32_t kOpq[2] = {1u, 0x80000000u};
-#endif
 PANIB_HD U64 make_u64(uint32_t lo, uint32_t hi) { return U64{lo, hi}; }
 PANIB_HD uint64_t to_u64(U64 x) { return ((uint64_t)x.hi << 32) | x.lo; }
 
@@ -143,36 +138,21 @@ PANIB_HD uint32_t shf_l(uint32_t lo, uint32_t hi, uint32_t s) {  // high 32 bits
 template <int R>
 PANIB_HD U64 rotl(U64 x) {
     static_assert(R > 0 && R < 64 && R != 32, "rotation amount");
-    if (R < 32) return U64{shf_l(x.hi, x.lo, R), shf_l(x.lo, x.hi, R)};
-    return U64{shf_l(x.lo, x.hi, R - 32), shf_l(x.hi, x.lo, R - 32)};  // swap halves, then rotate by R-32
+    if constexpr (R < 32) {
+        return U64{shf_l(x.hi, x.lo, R), shf_l(x.lo, x.hi, R)};
+    } else {  // swap halves, then rotate by R-32
+        return U64{shf_l(x.lo, x.hi, R - 32), shf_l(x.hi, x.lo, R - 32)};
+    }
 }
 
+// (Measured and rejected: doing the 64-bit adds and the `>> 33` of fmix on the FMA pipe through
+// IMAD.WIDE with multipliers ptxas cannot fold -- 5-15 % SLOWER; IMAD.WIDE/IMAD.HI are not cheap.)
 PANIB_HD U64 add64(U64 a, U64 b) {
-#if defined(__CUDA_ARCH__) && defined(PANIB_ADD_FMA)
-    // 64-bit add as IMAD.WIDE (a.lo * 1 + b) + IMAD (a.hi * 1 + carry-in high word): FMA pipe, not ALU pipe
-    uint32_t plo, phi, rhi;
-    const uint32_t one = kOpq[0];
-    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 q, {%3, %4};\n\tmad.wide.u32 p, %2, %5, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
-        : "=r"(plo), "=r"(phi) : "r"(a.lo), "r"(b.lo), "r"(b.hi), "r"(one));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(rhi) : "r"(a.hi), "r"(one), "r"(phi));
-    return U64{plo, rhi};
-#else
     const uint64_t r = to_u64(a) + to_u64(b);
     return U64{(uint32_t)r, (uint32_t)(r >> 32)};
-#endif
 }
 PANIB_HD U64 xor64(U64 a, U64 b) { return U64{a.lo ^ b.lo, a.hi ^ b.hi}; }
-PANIB_HD U64 xorshift33(U64 x) {  // x ^= x >> 33
-#if defined(__CUDA_ARCH__) && defined(PANIB_XS_WIDE)
-    // hi >> 1 as the upper half of hi * 2^31 (IMAD.WIDE on the FMA pipe instead of SHF on the ALU pipe)
-    uint32_t s, dummy;
-    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
-        : "=r"(dummy), "=r"(s) : "r"(x.hi), "r"(kOpq[1]));
-    return U64{x.lo ^ s, x.hi};
-#else
-    return U64{x.lo ^ (x.hi >> 1), x.hi};
-#endif
-}
+PANIB_HD U64 xorshift33(U64 x) { return U64{x.lo ^ (x.hi >> 1), x.hi}; }  // x ^= x >> 33
 PANIB_HD U64 fmix(U64 k) {
     k = xorshift33(k);
     k = mul_const<0xff51afd7ed558ccdULL>(k);
