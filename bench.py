@@ -50,6 +50,15 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures
+# profiles/r01_k1_ncu.md, r01_k2_ncu.md (config 2) and r01_k2c3_ncu.md (config 3); None = not captured.
+NCU_TRAFFIC_BYTES = {
+    ("config2", "k1"): 196.104192e6 + 7.778560e6,
+    ("config2", "k2"): 4.059136e6,
+    ("config3", "k2"): 40.328448e6 + 0.481536e6,
+}
+
+
 def hbm_peak() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.is_file():
@@ -406,12 +415,16 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     e2e_value = n_pairs / (e2e_t["ms"] * 1e-3) if e2e_t else None
     dominant_is_k1 = dev_t["k1_ms"] >= dev_t["k2_ms"]
     roof_k1 = {"kernel": "sketch_hash_kernel<31> (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peak,
-               "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
+               "unit": "GB/s", "frac": k1_gbs / peak,
+               "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k1")) if world == 1 else None,
+               "algorithmic_bytes": k1_bytes, "peak_source": peak_src,
                "ms_per_launch": k1_hash_ms, "bytes_per_bp": 0.25 + 0.125 + 8.0 / scaled,
                "note": "integer-ALU bound by construction (MurmurHash3 over 31 ASCII bytes per base); see "
                        "DESIGN.md and profiles/ for pipe utilisation"}
     roof_k2 = {"kernel": "intersect_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
-               "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k2_ms,
+               "frac": k2_gbs / peak,
+               "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k2")) if world == 1 else None,
+               "algorithmic_bytes": k2_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
                "bytes_per_pair": k2_bytes * world / max(1, n_pairs),
                "note": "algorithmic bytes 8(|A|+|B|)+4 per pair; staged queries and L2-resident columns make "
                        "DRAM traffic far smaller"}
