@@ -37,6 +37,10 @@ MANYSEARCH_HEADER = (
 )
 
 _engine = None
+# sketches written by prepare_genomes in this process, keyed by .sig path -> (mtime_ns, parsed signature):
+# compute_sourmash_tile then skips re-parsing ~90 KB of JSON per genome
+_sig_memo: dict[Path, tuple[int, dict]] = {}
+SIG_MEMO_MAX = 20_000
 
 
 def get_engine():  # noqa: ANN201
@@ -101,10 +105,13 @@ def prepare_genomes(logger: logging.Logger, run: db_orm.Run, cache: Path) -> Ite
         if pending:
             table = get_engine().sketch_genomes([recs for _, _, recs in pending], ksize, scaled)
             for (entry, fasta_filename, _), hashes in zip(pending, table.to_host(), strict=True):
-                sigfile.write_sig(
-                    cache / f"{entry.genome_hash}.sig", filename=str(fasta_filename), name=entry.genome_hash,
-                    ksize=ksize, max_hash=max_hash, hashes=hashes,
-                )
+                sig_path = cache / f"{entry.genome_hash}.sig"
+                sigfile.write_sig(sig_path, filename=str(fasta_filename), name=entry.genome_hash, ksize=ksize,
+                                  max_hash=max_hash, hashes=hashes)
+                if len(_sig_memo) < SIG_MEMO_MAX:
+                    _sig_memo[sig_path] = (sig_path.stat().st_mtime_ns, {
+                        "name": entry.genome_hash, "filename": str(fasta_filename), "ksize": ksize, "seed": 42,
+                        "max_hash": max_hash, "md5sum": sigfile.sketch_md5sum(hashes, ksize), "hashes": hashes})
                 yield entry
             pending.clear()
             pending_bytes = 0
@@ -235,7 +242,11 @@ def tile_arrays(  # noqa: PLR0913
         if not sig_path.is_file():
             msg = f"Missing sourmash signature file '{sig_path}'"
             log_sys_exit(logger, msg)
-        loaded[md5] = sigfile.read_sig(sig_path, ksize=int(m.group(1)) if m else None)
+        memo = _sig_memo.get(sig_path)
+        if memo is not None and memo[0] == sig_path.stat().st_mtime_ns:
+            loaded[md5] = memo[1]
+        else:
+            loaded[md5] = sigfile.read_sig(sig_path, ksize=int(m.group(1)) if m else None)
     if not loaded:
         empty = np.zeros((0, 0))
         return queries, subjects, empty.astype(np.uint32), empty, empty

@@ -19,16 +19,13 @@ SEED = 42
 
 def sketch_md5sum(hashes: np.ndarray, ksize: int) -> str:
     """sourmash's sketch checksum: md5 of ``str(ksize)`` followed by every hash in decimal."""
-    digest = hashlib.md5()  # noqa: S324
-    digest.update(str(ksize).encode())
-    for h in hashes.tolist():
-        digest.update(str(h).encode())
-    return digest.hexdigest()
+    return hashlib.md5((str(ksize) + "".join(map(str, hashes.tolist()))).encode()).hexdigest()  # noqa: S324
 
 
 def write_sig(path: Path, *, filename: str, name: str, ksize: int, max_hash: int, hashes: np.ndarray) -> None:
     """Write one single-sketch DNA signature file (same keys and key order as sourmash 4.8 / branchwater)."""
-    mins = hashes.astype(np.uint64).tolist()
+    mins = list(map(str, hashes.astype(np.uint64).tolist()))
+    md5sum = hashlib.md5((str(ksize) + "".join(mins)).encode()).hexdigest()  # noqa: S324
     head = {
         "class": "sourmash_signature",
         "email": "",
@@ -41,8 +38,8 @@ def write_sig(path: Path, *, filename: str, name: str, ksize: int, max_hash: int
     text = (
         "[{" + json.dumps(head, separators=(",", ":"))[1:-1]
         + ',"signatures":[{' + json.dumps(sketch_head, separators=(",", ":"))[1:-1]
-        + ',"mins":[' + ",".join(map(str, mins)) + "]"
-        + ',"md5sum":"' + sketch_md5sum(hashes, ksize) + '","molecule":"DNA"}],"version":0.4}]'
+        + ',"mins":[' + ",".join(mins) + "]"
+        + ',"md5sum":"' + md5sum + '","molecule":"DNA"}],"version":0.4}]'
     )
     tmp = path.with_suffix(path.suffix + ".tmp")
     tmp.write_text(text)

@@ -245,3 +245,37 @@ def test_full_size_genome_properties(eng) -> None:
     ident, _ = engine.ani_host(ov.astype(np.uint32), counts, counts, 31)
     assert ident[0, 1] == 1.0
     assert ov[2, 3] == len(np.intersect1d(left, right))
+
+
+def test_config2_full_size_against_oracle(eng) -> None:
+    """BASELINE configs[1] at FULL size: 100 synthetic 5 Mb genomes, k=31, scaled=1000.
+
+    Every sketch and the complete 100 x 100 intersection matrix against the oracle (the CPU port runs
+    the same workload in a couple of seconds on the host cores), plus ANI within 1e-12 / exactly.
+    """
+    from pyani_plus_b200 import engine
+
+    n, length, k, scaled = 100, 5_000_000, 31, 1000
+    d_ascii, tile_off = eng.synth_ascii_stream(SEED, 0, n, length)
+    table = eng.sketch_ascii_stream(d_ascii, tile_off, k, scaled, from_host=False)
+    del d_ascii
+    want_hashes, want_counts = oracle.synth_sketch_batch(SEED, 0, n, length, k, scaled)
+    got = table.to_host()
+    for g in range(n):
+        assert got[g].tolist() == want_hashes[g, : want_counts[g]].tolist(), g
+    want_ov = oracle.intersect_all(want_hashes, want_counts)
+    ov = eng.intersect(table).cpu().numpy()
+    assert (ov.astype(np.int64) == want_ov).all()
+    counts = table.counts.cpu().numpy()
+    ident, cov = engine.ani_host(ov.astype(np.uint32), counts, counts, k)
+    ident_d, cov_d = (t.cpu().numpy() for t in eng.ani_device(eng.intersect(table), table))
+    np.testing.assert_allclose(ident_d, ident, rtol=0, atol=ANI_ATOL, equal_nan=True)
+    np.testing.assert_allclose(cov_d, cov, rtol=0, atol=ANI_ATOL, equal_nan=True)
+    assert np.isnan(ident).sum() > 0  # distant pairs share no hash (NULL path) ...
+    assert (ident[~np.isnan(ident)] > 0.7).all() and (np.diag(ident) == 1.0).all()
+    for i, j in ((0, 1), (3, 77), (42, 42), (99, 0)):
+        row = oracle.pair_row(int(want_ov[i, j]), int(want_counts[i]), int(want_counts[j]), k)
+        if row is None:
+            assert np.isnan(ident[i, j])
+        else:
+            assert ident[i, j] == row["max_containment_ani"] and cov[i, j] == row["query_containment_ani"]

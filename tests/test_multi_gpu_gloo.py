@@ -86,7 +86,7 @@ def test_two_rank_gloo_pipeline() -> None:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    with mp.Manager() as manager:
+    with mp.get_context("spawn").Manager() as manager:
         out = manager.dict()
         mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
         whole, counts = out["whole"], out["counts"]
