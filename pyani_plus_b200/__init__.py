@@ -28,51 +28,43 @@ LOG_FILE_DYNAMIC = Path("--")  # internal use only, not exposed in CLI
 FASTA_EXTENSIONS = {".fasta", ".fas", ".fna", ".fa"}  # also with .gz appended
 
 
+_FILE_FORMAT = "%(asctime)s %(levelname)9s %(filename)21s:%(lineno)-3s | %(message)s"
+
+
+def _console_handler(level: int, *, plain: bool) -> logging.Handler:
+    """Terminal handler: plain stderr stream for workers, rich (stdout, with markup) for the public CLI."""
+    if plain:
+        handler: logging.Handler = logging.StreamHandler()
+        handler.setLevel(level)
+        return handler
+    from rich.logging import RichHandler  # noqa: PLC0415
+
+    return RichHandler(level=level, markup=True, omit_repeated_times=False, show_path=False,
+                       rich_tracebacks=True, tracebacks_suppress=["click"])
+
+
 def setup_logger(
     log_file: Path | None, *, terminal_level: int = logging.INFO, plain: bool = False
 ) -> logging.Logger:
-    """Return a file-based logger alongside a console logger (reference: __init__.py:61-117).
+    """Package logger with a console handler and, optionally, a DEBUG-level log file.
 
-    ``Path("-")`` or ``None`` means no log file.  The file handler is always at DEBUG level.
+    Same contract as the reference's ``setup_logger`` (``pyani_plus/__init__.py:61-117``): ``None`` or
+    ``Path("-")`` means no file; calling it again replaces the previous handlers; the file always
+    records DEBUG while the terminal shows ``terminal_level`` and up.
     """
     if log_file == LOG_FILE_DYNAMIC:
         sys.exit("ERROR: Internal flag value for dynamic log setting unresolved")
-    logger = logging.getLogger(f"{__package__}")
-    min_level = min(logging.DEBUG, terminal_level)
-    logger.setLevel(min_level)
-    if logger.hasHandlers():
-        logger.handlers.clear()
-    logging.basicConfig(level=min_level, format="%(message)s", datefmt="[%X]", handlers=[])
-
-    console_handler: logging.Handler
-    if plain:
-        console_handler = logging.StreamHandler()
-        console_handler.setLevel(terminal_level)
-    else:
-        from rich.logging import RichHandler  # noqa: PLC0415
-
-        console_handler = RichHandler(
-            level=terminal_level,
-            markup=True,
-            omit_repeated_times=False,
-            show_path=False,
-            rich_tracebacks=True,
-            tracebacks_suppress=["click"],
-        )
-    logger.addHandler(console_handler)
-
-    if log_file and log_file != Path("-"):
-        file_handler = logging.FileHandler(log_file, mode="a")
-        file_handler.setLevel(logging.DEBUG)
-        file_handler.setFormatter(
-            logging.Formatter(
-                fmt="%(asctime)s %(levelname)9s %(filename)21s:%(lineno)-3s | %(message)s",
-                datefmt="%Y-%m-%d %H:%M:%S",
-            )
-        )
-        logger.addHandler(file_handler)
-        msg = f"Logging to '{log_file}'"
-        logger.info(msg)
+    logger = logging.getLogger(__package__)
+    logger.handlers.clear()  # repeated set-up must not duplicate output
+    logger.setLevel(min(logging.DEBUG, terminal_level))
+    logger.addHandler(_console_handler(terminal_level, plain=plain))
+    wants_file = log_file is not None and log_file != Path("-")
+    if wants_file:
+        to_file = logging.FileHandler(log_file, mode="a")
+        to_file.setLevel(logging.DEBUG)
+        to_file.setFormatter(logging.Formatter(fmt=_FILE_FORMAT, datefmt="%Y-%m-%d %H:%M:%S"))
+        logger.addHandler(to_file)
+        logger.info("Logging to '%s'", log_file)  # shown on the terminal too
     else:
         logger.debug("Currently not logging to file.")
     return logger
