@@ -289,9 +289,23 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     result = {}
 
+    # several GPUs: finalize fused with the all-gather through peer-mapped memory when available
+    fused = None
+    if world > 1 and not args.nccl_gather:
+        fused = multi_gpu.SymmetricGather.create(per_rank, plan.row_stride, world, rank, dev)
+        ok = torch.tensor([1 if fused is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            fused = None
+
     def step(from_host: bool, marks: list | None = None) -> None:
         """One pass of the hot path; optional event marks after each stage."""
-        if from_host:
+        if fused is not None:
+            if from_host:
+                eng.hash_ascii_host(h_ascii, plan, bufs, tab, k)
+            else:
+                eng.hash_packed(plan, bufs, tab, k)
+        elif from_host:
             eng.sketch_ascii_host(h_ascii, plan, bufs, tab, k)
         else:
             eng.sketch_packed(plan, bufs, tab, k)
@@ -300,7 +314,10 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         max_count = size_hint
         if marks is not None:
             marks[0].record()
-        all_rows, all_counts = multi_gpu.all_gather_tables(tab["table"], tab["counts"], world)
+        if fused is not None:
+            all_rows, all_counts = fused.gather(eng, plan, tab)
+        else:
+            all_rows, all_counts = multi_gpu.all_gather_tables(tab["table"], tab["counts"], world)
         table = engine.SketchTable(all_rows, all_counts, k, scaled)
         if marks is not None:
             marks[1].record()
@@ -344,6 +361,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             t_k2.append(marks[1].elapsed_time(marks[2]))
             flush.fill_(1)  # L2 flush, outside the event pair
         barrier()
+        if os.environ.get("PANIB_BENCH_DEBUG"):
+            print(f"[rank {rank}] from_host={from_host} step ms {[round(x, 3) for x in tot]} "
+                  f"k1 {[round(x, 3) for x in t_k1]} gather {[round(x, 3) for x in t_gather]}", file=sys.stderr)
         wall = time.perf_counter() - wall0
         clocks = sampler.stop() if rank == 0 else None
         launches = eng.launch_count() - launches0
@@ -435,8 +455,10 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled,
                    "pairs": n_pairs, "seed": SEED, "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": f"genomes sliced over {world} rank(s) for K1, NCCL all-gather of sketch rows, "
-                                  "K2 work items round-robin" if world > 1 else "single GPU"},
+                   "parallelism": (f"genomes sliced over {world} ranks for K1, "
+                                   + ("finalize fused with the all-gather (peer-memory stores over NVLink)"
+                                      if fused is not None else "NCCL all-gather of sketch rows")
+                                   + ", K2 work items round-robin") if world > 1 else "single GPU"},
         "sketch_gbp_s": n * length / (dev_t["k1_ms"] * 1e-3) / 1e9,
         "pairs_per_s_k2": n_pairs / (dev_t["k2_ms"] * 1e-3),
         "stage_ms": {"k1_sketch": dev_t["k1_ms"], "allgather": dev_t["gather_ms"], "k2_intersect": dev_t["k2_ms"],
@@ -472,6 +494,8 @@ def main() -> None:
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="multi-GPU: plain NCCL all-gather instead of the fused finalize + peer-memory scatter")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

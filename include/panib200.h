@@ -118,6 +118,17 @@ PANIB_API int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d
 PANIB_API int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int64_t n_genomes, const int32_t *d_nb,
                           int32_t *d_counts, const int32_t *d_flags, int32_t *d_status, void *stream);
 
+/* Multi-GPU finalize FUSED with the all-gather of sketches: sorts the buckets of this rank's rows, then
+ * writes every genome's sorted sketch straight into row (rank*per_rank + g) of the gathered table of
+ * every rank through peer-mapped pointers (h_peer_tables[world], host array of device pointers that are
+ * valid on this device: CUDA IPC / symmetric memory), size in the row's last slot.  The caller issues a
+ * cross-rank barrier afterwards (multi_gpu.SymmetricGather).  Replaces panib_sketch_finalize + an NCCL
+ * all-gather of the rows. */
+PANIB_API int panib_sketch_finalize_gather(uint64_t *d_table, int64_t row_stride, int64_t n_genomes,
+                                 const int32_t *d_nb, int32_t *d_counts, const int32_t *d_flags,
+                                 int32_t *d_status, const uint64_t *const *h_peer_tables, int world, int rank,
+                                 int64_t per_rank, void *stream);
+
 /* Host-buffer form (what a caller holding FASTA bytes uses): copies the pinned ASCII stream
  * host->device on `stream`, packs it and sketches it.  d_ascii is device scratch of n_bases bytes,
  * n_bases = (n_tiles+1)*PANIB_TILE_BASES. */
@@ -127,6 +138,13 @@ PANIB_API int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii, 
                             const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
                             int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
                             void *stream);
+
+/* As panib_sketch_ascii_host without the finalize step (rows stay bucketed hash sets). */
+PANIB_API int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
+                                      uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
+                                      int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                                      const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                                      int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream);
 
 /* ---- stage 2 (kernel K2): all-vs-all sorted-sketch intersection -- replaces `manysearch` ---- */
 /* Queries are rows of (d_q_rows, d_q_counts, q_stride), subjects rows of (d_s_rows, ...); they may be

@@ -323,6 +323,53 @@ sketch_compact_kernel(uint64_t *__restrict__ table, int64_t row_stride, const in
     }
 }
 
+// finalize, step 2 fused with the all-gather of the multi-GPU path: instead of compacting a row in
+// place and handing the table to NCCL, the CTA writes the genome's sorted sketch straight into the
+// gathered table of EVERY rank (its own included) through peer-mapped pointers -- NVLink stores,
+// posted and coalesced, 8 bytes x 256 threads per instruction.  Row (rank*per_rank + g) of every
+// peer's table receives the hashes, with the size in the row's last slot; a symmetric-memory barrier
+// after the kernel (multi_gpu.SymmetricGather) publishes them.  This removes the separate NCCL
+// all-gather kernel and its extra pass over the sketches.
+constexpr int kMaxPeers = 16;
+struct PeerTables {
+    uint64_t *ptr[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256)
+sketch_compact_scatter_kernel(const uint64_t *__restrict__ table, int64_t row_stride,
+                              const int32_t *__restrict__ nb, int32_t *__restrict__ counts,
+                              const int32_t *__restrict__ flags, int32_t *status, PeerTables peers, int world,
+                              int64_t first_row) {
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const uint64_t *row = table + (size_t)g * row_stride;
+    const size_t dst_row = (size_t)(first_row + g) * row_stride;
+    const int n = nb[g];
+    int off = 0;
+    for (int b = 0; b < n; b++) {
+        const uint64_t *bucket = row + (size_t)b * kBucketSlots;
+        const int cnt = (int)bucket[kBucketSlots - 1];
+        for (int i = tid; i < cnt; i += 256) {
+            const uint64_t v = bucket[i];
+            for (int r = 0; r < world; r++) peers.ptr[r][dst_row + off + i] = v;
+        }
+        off += cnt;
+    }
+    if (tid == 0) {
+        if ((flags[g] & 1) && off < row_stride - 1) {  // the all-ones hash (scaled == 1 only)
+            for (int r = 0; r < world; r++) peers.ptr[r][dst_row + off] = kEmpty;
+            off++;
+        }
+        counts[g] = off;
+        if (off < row_stride) {
+            for (int r = 0; r < world; r++) peers.ptr[r][dst_row + row_stride - 1] = (uint64_t)off;
+        } else if (status) {
+            atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);
+        }
+        if (status) atomicMax(status + 1, off);
+    }
+    __threadfence_system();  // order the peer stores before the kernel-end / barrier signal
+}
+
 }  // namespace panib
 
 // ================================================================================================
@@ -432,6 +479,30 @@ extern "C" int panib_sketch_finalize(uint64_t *d_table, int64_t row_stride, int6
     return check_launch("sketch_compact_kernel");
 }
 
+extern "C" int panib_sketch_finalize_gather(uint64_t *d_table, int64_t row_stride, int64_t n_genomes,
+                                            const int32_t *d_nb, int32_t *d_counts, const int32_t *d_flags,
+                                            int32_t *d_status, const uint64_t *const *h_peer_tables, int world,
+                                            int rank, int64_t per_rank, void *stream) {
+    if (n_genomes <= 0) return PANIB_OK;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !h_peer_tables || n_genomes > per_rank) {
+        set_error("panib_sketch_finalize_gather: bad world/rank/per_rank (%d/%d/%lld)", world, rank,
+                  (long long)per_rank);
+        return PANIB_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned nbmax = (unsigned)(row_stride / kBucketSlots);
+    const unsigned gy = (unsigned)(n_genomes < 65535 ? n_genomes : 65535);
+    sketch_sort_buckets_kernel<<<dim3(nbmax, gy), 256, 0, st>>>(d_table, row_stride, (int)n_genomes, d_nb, d_status);
+    int rc = check_launch("sketch_sort_buckets_kernel");
+    if (rc) return rc;
+    PeerTables peers;
+    for (int r = 0; r < kMaxPeers; r++) peers.ptr[r] = r < world ? const_cast<uint64_t *>(h_peer_tables[r]) : nullptr;
+    sketch_compact_scatter_kernel<<<(unsigned)n_genomes, 256, 0, st>>>(d_table, row_stride, d_nb, d_counts, d_flags,
+                                                                       d_status, peers, world,
+                                                                       (int64_t)rank * per_rank);
+    return check_launch("sketch_compact_scatter_kernel");
+}
+
 extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
                                    int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
                                    const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
@@ -447,12 +518,11 @@ extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_m
 // copy stream while chunk c is packed and hashed on the caller's stream, so that the PCIe transfer
 // (1 byte per base) and K1 overlap.  K1 of a chunk stops one tile short of the chunk's end, because
 // the last tile's k-1 halo lives in the next chunk; that tile is hashed with the next chunk.
-extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
-                                       uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
-                                       int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
-                                       const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
-                                       int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
-                                       void *stream) {
+static int sketch_ascii_host_impl(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases, uint32_t *d_packed,
+                                  uint32_t *d_mask, const int64_t *d_tile_off, int64_t n_genomes, int64_t n_tiles,
+                                  int k, uint32_t seed, uint64_t max_hash, const int32_t *d_nb,
+                                  const uint64_t *d_bmul, uint64_t *d_table, int64_t row_stride, int32_t *d_counts,
+                                  int32_t *d_flags, int32_t *d_status, void *stream, bool finalize) {
     if (n_bases != (n_tiles + 1) * (int64_t)kTileBases) {
         set_error("n_bases=%lld must equal (n_tiles+1)*%d", (long long)n_bases, kTileBases);
         return PANIB_E_ARG;
@@ -505,5 +575,30 @@ extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii,
         if (rc) return rc;
         if (upto > hashed) hashed = upto;
     }
+    if (!finalize) return PANIB_OK;
     return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, d_status, stream);
+}
+
+extern "C" int panib_sketch_ascii_host(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
+                                       uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
+                                       int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                                       const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                                       int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
+                                       void *stream) {
+    return sketch_ascii_host_impl(h_ascii, d_ascii, n_bases, d_packed, d_mask, d_tile_off, n_genomes, n_tiles, k,
+                                  seed, max_hash, d_nb, d_bmul, d_table, row_stride, d_counts, d_flags, d_status,
+                                  stream, true);
+}
+
+// same, but the rows are left as sorted-per-bucket hash sets: the caller finalizes them itself
+// (panib_sketch_finalize or, on several GPUs, panib_sketch_finalize_gather)
+extern "C" int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t *d_ascii, int64_t n_bases,
+                                                 uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
+                                                 int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed,
+                                                 uint64_t max_hash, const int32_t *d_nb, const uint64_t *d_bmul,
+                                                 uint64_t *d_table, int64_t row_stride, int32_t *d_flags,
+                                                 int32_t *d_status, void *stream) {
+    return sketch_ascii_host_impl(h_ascii, d_ascii, n_bases, d_packed, d_mask, d_tile_off, n_genomes, n_tiles, k,
+                                  seed, max_hash, d_nb, d_bmul, d_table, row_stride, nullptr, d_flags, d_status,
+                                  stream, false);
 }

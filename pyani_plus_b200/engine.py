@@ -77,6 +77,11 @@ def load_library() -> ctypes.CDLL:
     L.panib_sketch_finalize.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
     L.panib_sketch_ascii_host.restype = _i32
     L.panib_sketch_ascii_host.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp, _vp]
+    L.panib_sketch_ascii_host_hash_only.restype = _i32
+    L.panib_sketch_ascii_host_hash_only.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp]
+    L.panib_sketch_finalize_gather.restype = _i32
+    L.panib_sketch_finalize_gather.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i32, _i32,
+                                               _i64, _vp]
     L.panib_intersect.restype = _i32
     L.panib_intersect.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i32, _u64, _i64, _i32, _i32,
                                   _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp]
@@ -300,6 +305,32 @@ class Engine:
         """H2D copy of a pinned ASCII stream + pack + K1 in one C-ABI call (enqueue only)."""
         _check(self.lib.panib_sketch_ascii_host(h_ascii.data_ptr(), bufs["ascii"].data_ptr(), plan.n_bases,
                                                 *self._sketch_args(plan, bufs, tab, k, seed)))
+
+    def hash_packed(self, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42) -> None:
+        """K1 hashing only: rows are left as bucketed hash sets (finalize separately)."""
+        a = self._sketch_args(plan, bufs, tab, k, seed)
+        _check(self.lib.panib_sketch_hash_only(*a[:12], a[13], a[14], a[15]))
+
+    def hash_ascii_host(self, h_ascii, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42) -> None:
+        """H2D + pack + K1 hashing only (finalize separately)."""
+        a = self._sketch_args(plan, bufs, tab, k, seed)
+        _check(self.lib.panib_sketch_ascii_host_hash_only(h_ascii.data_ptr(), bufs["ascii"].data_ptr(),
+                                                          plan.n_bases, *a[:12], a[13], a[14], a[15]))
+
+    def finalize(self, plan: "StreamPlan", tab: dict) -> None:
+        """Sort / dedup / compact the rows in place (single-GPU finalize)."""
+        _check(self.lib.panib_sketch_finalize(tab["table"].data_ptr(), plan.row_stride, plan.n_genomes,
+                                              plan.d_nb.data_ptr(), tab["counts"].data_ptr(),
+                                              tab["flags"].data_ptr(), self.status.data_ptr(), self._stream()))
+
+    def finalize_gather(self, plan: "StreamPlan", tab: dict, peer_ptrs: list[int], rank: int, per_rank: int) -> None:
+        """Finalize fused with the all-gather: sorted sketches are written into every rank's gathered
+        table through the peer pointers (``multi_gpu.SymmetricGather``)."""
+        arr = (_vp * len(peer_ptrs))(*peer_ptrs)
+        _check(self.lib.panib_sketch_finalize_gather(
+            tab["table"].data_ptr(), plan.row_stride, plan.n_genomes, plan.d_nb.data_ptr(),
+            tab["counts"].data_ptr(), tab["flags"].data_ptr(), self.status.data_ptr(), arr, len(peer_ptrs), rank,
+            per_rank, self._stream()))
 
     def check_status(self) -> int:
         """Synchronise and return (then clear) the PANIB_ST_* bits kernels raised."""

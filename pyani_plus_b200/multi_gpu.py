@@ -64,6 +64,49 @@ def all_gather_tables(rows, counts, world: int, *, sizes_in_last_slot: bool = Tr
     return all_rows, all_counts
 
 
+class SymmetricGather:
+    """Gathered sketch table in peer-mapped (symmetric) memory: the fused finalize + all-gather.
+
+    Every rank allocates the same ``[world * per_rank, stride]`` table with
+    ``torch.distributed._symmetric_memory`` and exchanges the peer pointers once.  Per step,
+    ``Engine.finalize_gather`` makes each rank's finalize kernel store its sorted sketches directly
+    into all ranks' tables over NVLink, bracketed by two symmetric-memory barriers (before: nobody is
+    still reading the table from the previous step; after: all stores have landed).  No NCCL kernel and
+    no second pass over the sketches.  ``available()`` is False when symmetric memory cannot be set up
+    (then ``all_gather_tables`` = NCCL is used; that is a transport choice, not a CPU fallback).
+    """
+
+    def __init__(self, per_rank: int, stride: int, world: int, rank: int, device) -> None:  # noqa: ANN001
+        import torch  # noqa: PLC0415
+        import torch.distributed as dist  # noqa: PLC0415
+        import torch.distributed._symmetric_memory as symm  # noqa: PLC0415
+
+        self.world, self.rank, self.per_rank, self.stride = world, rank, per_rank, stride
+        self.rows = symm.empty((world * per_rank, stride), dtype=torch.int64, device=device)
+        self.handle = symm.rendezvous(self.rows, dist.group.WORLD)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.peer_ptrs) != world or self.peer_ptrs[rank] != self.rows.data_ptr():
+            msg = "symmetric memory rendezvous returned unexpected pointers"
+            raise RuntimeError(msg)
+
+    @classmethod
+    def create(cls, per_rank: int, stride: int, world: int, rank: int, device):  # noqa: ANN001, ANN206
+        """The gather object, or None when symmetric memory is unavailable on this system."""
+        try:
+            return cls(per_rank, stride, world, rank, device)
+        except Exception:  # noqa: BLE001
+            return None
+
+    def gather(self, eng, plan, tab: dict):  # noqa: ANN001, ANN201
+        """Finalize this rank's rows and scatter them to all ranks; returns (all_rows, all_counts)."""
+        import torch  # noqa: PLC0415
+
+        self.handle.barrier(channel=0)  # nobody still reads the table of the previous step
+        eng.finalize_gather(plan, tab, self.peer_ptrs, self.rank, self.per_rank)
+        self.handle.barrier(channel=1)  # every rank's stores have landed
+        return self.rows, self.rows[:, -1].to(torch.int32).contiguous()
+
+
 def item_owner(item_id: int, world: int) -> int:
     """Rank that processes K2 work item ``item_id`` (mirrors ``id % world`` in intersect_kernel)."""
     return item_id % world
