@@ -340,32 +340,28 @@ sketch_compact_scatter_kernel(const uint64_t *__restrict__ table, int64_t row_st
                               const int32_t *__restrict__ nb, int32_t *__restrict__ counts,
                               const int32_t *__restrict__ flags, int32_t *status, PeerTables peers, int world,
                               int64_t first_row) {
-    const int g = blockIdx.x, tid = threadIdx.x;
+    // grid = (genome, peer): many CTAs keep enough NVLink stores in flight (the local re-reads of the
+    // sorted buckets hit L2)
+    const int g = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
     const uint64_t *row = table + (size_t)g * row_stride;
-    const size_t dst_row = (size_t)(first_row + g) * row_stride;
+    uint64_t *dst = peers.ptr[r] + (size_t)(first_row + g) * row_stride;
     const int n = nb[g];
     int off = 0;
     for (int b = 0; b < n; b++) {
         const uint64_t *bucket = row + (size_t)b * kBucketSlots;
         const int cnt = (int)bucket[kBucketSlots - 1];
-        for (int i = tid; i < cnt; i += 256) {
-            const uint64_t v = bucket[i];
-            for (int r = 0; r < world; r++) peers.ptr[r][dst_row + off + i] = v;
-        }
+#pragma unroll 4
+        for (int i = tid; i < cnt; i += 256) dst[off + i] = bucket[i];
         off += cnt;
     }
     if (tid == 0) {
-        if ((flags[g] & 1) && off < row_stride - 1) {  // the all-ones hash (scaled == 1 only)
-            for (int r = 0; r < world; r++) peers.ptr[r][dst_row + off] = kEmpty;
-            off++;
+        if ((flags[g] & 1) && off < row_stride - 1) dst[off++] = kEmpty;  // the all-ones hash (scaled == 1 only)
+        if (off < row_stride) dst[row_stride - 1] = (uint64_t)off;
+        if (r == 0) {
+            counts[g] = off;
+            if (off >= row_stride && status) atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);
+            if (status) atomicMax(status + 1, off);
         }
-        counts[g] = off;
-        if (off < row_stride) {
-            for (int r = 0; r < world; r++) peers.ptr[r][dst_row + row_stride - 1] = (uint64_t)off;
-        } else if (status) {
-            atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);
-        }
-        if (status) atomicMax(status + 1, off);
     }
     __threadfence_system();  // order the peer stores before the kernel-end / barrier signal
 }
@@ -497,10 +493,15 @@ extern "C" int panib_sketch_finalize_gather(uint64_t *d_table, int64_t row_strid
     if (rc) return rc;
     PeerTables peers;
     for (int r = 0; r < kMaxPeers; r++) peers.ptr[r] = r < world ? const_cast<uint64_t *>(h_peer_tables[r]) : nullptr;
-    sketch_compact_scatter_kernel<<<(unsigned)n_genomes, 256, 0, st>>>(d_table, row_stride, d_nb, d_counts, d_flags,
-                                                                       d_status, peers, world,
-                                                                       (int64_t)rank * per_rank);
-    return check_launch("sketch_compact_scatter_kernel");
+    for (int64_t g0 = 0; g0 < n_genomes; g0 += 65535) {  // grid.x limit is fine, keep y = peers
+        const int64_t ng = n_genomes - g0 < 65535 ? n_genomes - g0 : 65535;
+        sketch_compact_scatter_kernel<<<dim3((unsigned)ng, (unsigned)world), 256, 0, st>>>(
+            d_table + (size_t)g0 * row_stride, row_stride, d_nb + g0, d_counts + g0, d_flags + g0, d_status, peers,
+            world, (int64_t)rank * per_rank + g0);
+        rc = check_launch("sketch_compact_scatter_kernel");
+        if (rc) return rc;
+    }
+    return PANIB_OK;
 }
 
 extern "C" int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
