@@ -52,8 +52,9 @@ static int64_t run(const uint32_t *packed, const uint32_t *mask, int64_t t0, int
         for (int i = 0; i < kTileMaskWords; i++) any |= sm[i];
         for (int tid = 0; tid < kThreadsK1; tid++) {
             const int u = tid >> 2, a = tid & 3;
-            if (any) hash_thread_kmers<K, true>(sp, sm, u, a, seed, c);
-            else hash_thread_kmers<K, false>(sp, sm, u, a, seed, c);
+            uint32_t blk[2 * kBlkWords];  // the thread's scratch block (shared memory on the GPU)
+            if (any) hash_thread_kmers<K, true>(sp, sm, blk, 1, u, a, seed, c);
+            else hash_thread_kmers<K, false>(sp, sm, blk, 1, u, a, seed, c);
         }
     }
     return c.n;

@@ -261,13 +261,23 @@ PANIB_HD uint64_t window(const uint32_t *X, int off) {
 // Hash the 16 k-mers of thread (u, a) of a tile.
 //   sp   : packed words of the tile (word 0 bit 0 = tile position 0), kTileWords valid words
 //   sm   : validity-mask words of the tile (bit set = invalid), kTileMaskWords valid words
+//   blk  : this thread's private scratch of 2*kBlkWords words (shared memory on the GPU, words of
+//          consecutive threads kBlkWords apart: odd stride = bank-conflict free)
 //   emit : callable(uint64_t h) invoked for every VALID k-mer (caller applies the max_hash test)
 // DIRTY=false skips the per-k-mer validity test (caller guarantees the tile has no invalid base).
+//
+// The ASCII form of the thread's span (both strands) is written ONCE to the thread's scratch block;
+// k-mer j then reads its NWD words from `fwd ? blk + j : blk + kBlkWords + 15 - j`: the canonical
+// choice costs one address select and the words arrive through the (otherwise idle) load/store pipe,
+// instead of NWD SEL instructions on the ALU pipe, which is the pipe that limits K1.
+constexpr int kBlkWords = 23;  // ASCII words per strand of a span: ceil((60 + 32) / 4), odd on purpose
+
 template <int K, bool DIRTY, class Emit>
-PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, int a, uint32_t seed,
-                                Emit &&emit) {
+PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, uint32_t *blk, int blk_stride, int u, int a,
+                                uint32_t seed, Emit &&emit) {
     using G_ = Geom<K>;
     constexpr int NX = G_::NX, NA = G_::NA, NWD = G_::NWD;
+    static_assert(NA <= kBlkWords, "scratch block too small");
     const uint32_t *src = sp + (kKmersPerThread / 4) * u;  // span starts at tile position 4*KPT*u + a
     uint32_t X[NX];
 #pragma unroll
@@ -289,28 +299,27 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, i
         Xr[w] = sh ? shf_r(l, h, sh) : l;
     }
 
-    // ASCII expansion of both strands: each base is expanded once per thread, but LAZILY -- one packed
-    // word (4 ASCII registers) of each strand right before the first k-mer that needs it -- so that
-    // only ~NWD+4 ASCII registers per strand are live at a time (register pressure decides how many
-    // warps are resident, and K1 is latency bound: more warps = more throughput).
-    uint32_t G[4 * NX], H[4 * NX];
+    // ASCII expansion of both strands, each base once per thread, straight into the scratch block
+    // (element e of the block lives at blk[e * blk_stride]: stride 1 on the host, blockDim on the GPU
+    // so that a warp's accesses to the same element are consecutive words)
+    uint32_t *fw = blk, *rv = blk + kBlkWords * blk_stride;
+#pragma unroll
+    for (int w = 0; w < NX; w++) {
+        if (4 * w < NA) {
+            uint32_t e[4];
+            expand16(X[w], e);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (4 * w + i < NA) fw[(4 * w + i) * blk_stride] = e[i];
+            expand16(Xr[w], e);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (4 * w + i < NA) rv[(4 * w + i) * blk_stride] = e[i];
+        }
+    }
+
 #pragma unroll
     for (int j = 0; j < kKmersPerThread; j++) {
-        // forward strand: k-mer j reads G[j .. j+NWD)
-        {
-            const int hi_w = (j + NWD - 1) >> 2;               // last packed word needed by this k-mer
-            const int lo_w = j == 0 ? 0 : ((j + NWD - 2) >> 2) + 1;  // first word not yet expanded
-#pragma unroll
-            for (int w = lo_w; w <= hi_w; w++) expand16(X[w], &G[4 * w]);
-        }
-        // reverse strand: k-mer j reads H[15-j .. 15-j+NWD)
-        {
-            const int b = kKmersPerThread - 1 - j;
-            const int lo_w = b >> 2;
-            const int hi_w = j == 0 ? (b + NWD - 1) >> 2 : ((b + 1) >> 2) - 1;  // words below the previous k-mer's
-#pragma unroll
-            for (int w = lo_w; w <= hi_w; w++) expand16(Xr[w], &H[4 * w]);
-        }
         bool valid = true;
         if (DIRTY) {
             const int pos = 4 * kKmersPerThread * u + a + 4 * j;
@@ -320,14 +329,13 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, int u, i
         }
         const uint64_t F = window<K, NX>(X, 8 * j);
         const uint64_t R = window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
-        const bool fwd = F < R;
+        const uint32_t *words = F < R ? fw + j * blk_stride : rv + (kKmersPerThread - 1 - j) * blk_stride;
         uint32_t W[NWD];
 #pragma unroll
-        for (int i = 0; i < NWD; i++) W[i] = fwd ? G[j + i] : H[kKmersPerThread - 1 - j + i];
+        for (int i = 0; i < NWD; i++) W[i] = words[i * blk_stride];
         const uint64_t h = murmur_words<K>(W, seed);
         if (!DIRTY || valid) emit(h);
     }
-    (void)NA;
 }
 
 }  // namespace panib

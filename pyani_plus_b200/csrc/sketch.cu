@@ -119,6 +119,9 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     // persistent CTAs, double buffer, two barriers per CTA tile
     __shared__ __align__(16) uint32_t sp[2][kTileWords];
     __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
+    // per-thread ASCII scratch, element-major: element e of thread t at blk[e * kThreadsK1 + t]
+    extern __shared__ uint32_t blk_all[];  // kK1DynSmem bytes
+    uint32_t *blk = blk_all + threadIdx.x;
     constexpr int S = kTileBases / kCtaTile;
     n_tiles *= S;
     int64_t tile = tile_begin * S + blockIdx.x;
@@ -151,9 +154,9 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g,
                          status};
         if (!dirty) {
-            hash_thread_kmers<K, false>(sp[cur], sm[cur], u, a, seed, emit);
+            hash_thread_kmers<K, false>(sp[cur], sm[cur], blk, kThreadsK1, u, a, seed, emit);
         } else {
-            hash_thread_kmers<K, true>(sp[cur], sm[cur], u, a, seed, emit);
+            hash_thread_kmers<K, true>(sp[cur], sm[cur], blk, kThreadsK1, u, a, seed, emit);
         }
         __syncthreads();
     }
@@ -379,6 +382,8 @@ static dim3 tile_grid(int64_t n_tiles) {  // one CTA per tile (generic kernel); 
     return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
+constexpr size_t kK1DynSmem = 2 * kBlkWords * kThreadsK1 * sizeof(uint32_t);  // per-thread ASCII scratch
+
 // persistent grid of the fast kernel: SMs x resident CTAs per SM
 template <int K>
 static int persistent_grid(int64_t n_tiles) {
@@ -387,7 +392,8 @@ static int persistent_grid(int64_t n_tiles) {
         int dev = 0, sms = 148, per_sm = 2;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K>, kThreadsK1, 0) !=
+        cudaFuncSetAttribute(sketch_hash_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1DynSmem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K>, kThreadsK1, kK1DynSmem) !=
                 cudaSuccess || per_sm < 1)
             per_sm = 2;
         cached = sms * per_sm;
@@ -418,7 +424,7 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
     const int64_t n = tile_end - tile_begin;
     if (n <= 0) return PANIB_OK;
 #define PANIB_LAUNCH_K(KK)                                                                                   \
-    sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, 0, st>>>(                                    \
+    sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, kK1DynSmem, st>>>(                                    \
         d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, seed, max_hash, d_nb, d_bmul,    \
         d_table, row_stride, d_flags, d_status)
     switch (k) {
