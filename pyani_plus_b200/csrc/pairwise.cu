@@ -149,11 +149,23 @@ __global__ void __launch_bounds__(kThreadsK2) intersect_kernel(const K2Args a) {
         for (int q = blast + 1 + tid; q <= R; q += kThreadsK2) idx[q] = (uint16_t)n;
     }
     __syncthreads();
-    for (int q = tid; q < R; q += kThreadsK2) {  // flag the buckets with more than two elements
-        const uint32_t lo = idx[q] & 0x7FFFu, hi = idx[q + 1] & 0x7FFFu;
-        if (hi - lo > 2u) idx[q] = (uint16_t)(lo | kIdxMany);
+    // flag the buckets with more than two elements.  A neighbour's entry is read to decide, so
+    // deciding and writing are separated by a barrier, 32 buckets per thread (one mask register) at a
+    // time: one round for R <= 16384.
+    for (int q0 = 0; q0 < R; q0 += 32 * kThreadsK2) {
+        uint32_t many = 0;
+#pragma unroll 4
+        for (int it = 0; it < 32; ++it) {
+            const int q = q0 + it * kThreadsK2 + tid;
+            if (q < R && (uint32_t)idx[q + 1] - (uint32_t)idx[q] > 2u) many |= 1u << it;
+        }
+        __syncthreads();
+        for (; many; many &= many - 1) {
+            const int q = q0 + (__ffs(many) - 1) * kThreadsK2 + tid;
+            idx[q] = (uint16_t)(idx[q] | kIdxMany);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- each warp streams subject columns (sorted, so neighbouring lanes probe neighbouring slots)
     const int lane = tid & 31, warp = tid >> 5;
