@@ -279,3 +279,41 @@ def test_config2_full_size_against_oracle(eng) -> None:
             assert np.isnan(ident[i, j])
         else:
             assert ident[i, j] == row["max_containment_ani"] and cov[i, j] == row["query_containment_ani"]
+
+
+def test_edge_shapes_vs_oracle(eng) -> None:
+    """Odd workloads: thousands of tiny genomes, one very large genome (multi-cell K2, >100 buckets),
+    repeats (set semantics at insert), all-N and empty genomes, very unequal sketch sizes."""
+    from pyani_plus_b200 import engine
+
+    rng = np.random.default_rng(99)
+    k, scaled = 31, 100
+    big = oracle.synth_genome(SEED, 5, 12_000_000)  # ~120,000 hashes: several K2 cells
+    genomes: list[list[bytes]] = [
+        [big],
+        [big[:6_000_000], big[6_000_000:]],  # same bases as two records (loses 30 spanning k-mers)
+        [b"ACGT" * 50_000],  # 4 distinct k-mers, 200,000 windows
+        [b"A" * 100_000],
+        [b"N" * 5_000],
+        [b"ACGTTGCA" * 3 + b"N" + b"GATTACA" * 9],
+        [],
+    ]
+    tiny = [bytes(rng.choice(list(b"ACGT"), 2_000).astype(np.uint8)) for _ in range(1500)]
+    genomes += [[t] for t in tiny]
+    table = eng.sketch_genomes(genomes, k, scaled)
+    got = table.to_host()
+    for g in (0, 1, 2, 3, 4, 5, 6, 7, 8, 1506):
+        assert got[g].tolist() == oracle.sketch_records(genomes[g], k, scaled, fast=True).tolist(), g
+    assert len(got[4]) == 0 and len(got[6]) == 0 and len(got[0]) > 110_000
+    assert abs(len(got[0]) - len(got[1])) <= 2
+    ov = eng.intersect(table).cpu().numpy()
+    n = len(genomes)
+    assert ov.shape == (n, n) and (ov == ov.T).all()
+    assert (np.diag(ov) == [len(x) for x in got]).all()
+    sample = [(0, 1), (0, 2), (1, 0), (0, 7), (7, 8), (2, 3), (4, 4), (0, 1506), (5, 0), (100, 1200)]
+    for i, j in sample:
+        assert ov[i, j] == oracle.intersect(got[i], got[j]), (i, j)
+    counts = table.counts.cpu().numpy()
+    ident, cov = engine.ani_host(ov.astype(np.uint32), counts, counts, k)
+    assert np.isnan(ident[4, 4]) and np.isnan(ident[6, 6])  # empty sketches: no self row
+    assert ident[0, 0] == 1.0 and ident[0, 1] == ident[1, 0] and cov[1, 0] >= cov[0, 1]
