@@ -1,0 +1,32 @@
+"""Parity at BASELINE.json's full sizes (SURVEY.md 8d "Parity at scale").
+
+config 3 (1000 x 5 Mb): every sketch and the complete 1000 x 1000 count matrix against the oracle.
+config 5 (2000 x 5 Mb, scaled=100) and config 4 (10 000 x 5 Mb): the GPU runs the FULL workload; the
+oracle checks blocks of genomes spread over the id range (all their hashes, their sub-matrix of the
+full count matrix) and the whole matrix must satisfy the size-independent properties (symmetric,
+diagonal = sketch size, ov <= min size).  ``tools/parity_at_scale.py`` runs the same check with any
+sample size; profiles/r01_parity_at_scale.md records the complete runs.
+"""
+
+from __future__ import annotations
+
+import pytest
+
+from tools.parity_at_scale import check_workload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize(("workload", "sample"), [("config3", 0), ("config5", 208), ("config4", 256)])
+def test_baseline_config_against_oracle(workload: str, sample: int) -> None:
+    import torch
+
+    if workload == "config4" and torch.cuda.mem_get_info(0)[1] < 60 << 30:
+        pytest.skip("needs a 64 GB+ GPU")
+    report = check_workload(workload, sample)
+    assert report["sketches_with_mismatch"] == 0, report
+    assert report["count_cells_with_mismatch"] == 0, report
+    assert report["ani_device_vs_host_max_abs_err"] <= 1e-12, report
+    assert report["ani_host_rows_not_equal_oracle"] == 0, report
+    assert report["ok"], report
+    assert report["whole_matrix"]["null_pairs"] > 0  # distant descendants share no hash (NULL path)
