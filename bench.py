@@ -298,61 +298,63 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         if not int(ok.item()):
             fused = None
 
-    def step(from_host: bool, marks: list | None = None) -> None:
-        """One pass of the hot path; optional event marks after each stage."""
-        if fused is not None:
-            if from_host:
-                eng.hash_ascii_host(h_ascii, plan, bufs, tab, k)
-            else:
-                eng.hash_packed(plan, bufs, tab, k)
-        elif from_host:
-            eng.sketch_ascii_host(h_ascii, plan, bufs, tab, k)
+    from pyani_plus_b200 import pipeline
+
+    stepper = pipeline.SourmashStep(eng, plan, bufs, tab, k, world=world, rank=rank, gather=fused,
+                                    size_hint=size_hint, h_ascii=h_ascii)
+    # the step as ONE CUDA graph launch (all ranks must agree, the gather has barriers inside)
+    graphed: dict = {}
+    per_step_launches: dict = {}
+    if not args.no_graph:
+        for from_host in ((False, True) if do_e2e else (False,)):
+            l0 = eng.launch_count()
+            ok = stepper.capture(from_host=from_host, to_host=from_host)
+            per_step_launches[from_host] = (eng.launch_count() - l0) // 2  # warm-up run + capture
+            ok_t = torch.tensor([1 if ok else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+            graphed[from_host] = bool(int(ok_t.item()))
+
+    def step(from_host: bool, marks: list | None = None, *, graph: bool = False) -> None:
+        """One pass of the hot path (product API: pipeline.SourmashStep), status checked at the end."""
+        if graph:
+            stepper.replay(from_host=from_host, to_host=from_host)
         else:
-            eng.sketch_packed(plan, bufs, tab, k)
-        # no read-back between the stages: K2's shared memory is sized from the genome lengths (the
-        # kernel verifies it), K1's overflow bit is read together with K2's at the end of the step
-        max_count = size_hint
-        if marks is not None:
-            marks[0].record()
-        if fused is not None:
-            all_rows, all_counts = fused.gather(eng, plan, tab)
-        else:
-            all_rows, all_counts = multi_gpu.all_gather_tables(tab["table"], tab["counts"], world)
-        table = engine.SketchTable(all_rows, all_counts, k, scaled)
-        if marks is not None:
-            marks[1].record()
-        ov = eng.intersect(table, rank=rank, world=world, max_count=max_count)
-        if marks is not None:
-            marks[2].record()
-        ident, cov = eng.ani_device(ov, table)
+            stepper.enqueue(from_host=from_host, marks=marks, to_host=from_host)
+        stepper.finish()
+        out = stepper.out
         if from_host:
-            result["identity"] = ident.cpu()
-            result["cov_query"] = cov.cpu()
-            result["counts"] = table.counts.cpu()
+            result["identity"], result["cov_query"] = out["identity_host"], out["cov_query_host"]
+            result["counts"] = out["counts_host"]
         else:
-            result["ov"], result["table"] = ov, table
+            result["ov"], result["table"] = out["ov"], out["table"]
 
     def barrier() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(from_host: bool, steps: int, warmup: int) -> dict:
+    def timed_loop(from_host: bool, steps: int, warmup: int, *, graph: bool = False) -> dict:
         for _ in range(warmup):
-            step(from_host)
+            step(from_host, graph=graph)
             flush.fill_(1)
-        barrier()
-        launches0 = eng.launch_count()
-        tot, t_k1, t_gather, t_k2 = [], [], [], []
+        # the clock sampler starts BEFORE the barrier: starting it costs rank 0 a millisecond or two, which
+        # every other rank would otherwise wait for inside the first timed step's gather
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        barrier()
+        launches0 = eng.launch_count()
+        tot, t_k1, t_gather, t_k2 = [], [], [], []
         wall0 = time.perf_counter()
         for _ in range(steps):
             e0, e1 = ev(), ev()
             marks = [ev(), ev(), ev()]
             e0.record()
-            step(from_host, marks)
+            step(from_host, None if graph else marks, graph=graph)
+            if graph:
+                for m in marks:  # no stage marks inside a graph launch
+                    m.record()
             e1.record()
             e1.synchronize()
             tot.append(e0.elapsed_time(e1))
@@ -366,7 +368,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                   f"k1 {[round(x, 3) for x in t_k1]} gather {[round(x, 3) for x in t_gather]}", file=sys.stderr)
         wall = time.perf_counter() - wall0
         clocks = sampler.stop() if rank == 0 else None
-        launches = eng.launch_count() - launches0
+        launches = eng.launch_count() - launches0 + (steps * per_step_launches[from_host] if graph else 0)
         stats = torch.tensor([sum(tot), sum(t_k1), sum(t_gather), sum(t_k2), float(launches)],
                              dtype=torch.float64, device=dev)
         if world > 1:
@@ -379,7 +381,10 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         return {"ms": s[0] / steps, "k1_ms": s[1] / steps, "gather_ms": s[2] / steps, "k2_ms": s[3] / steps,
                 "launches": int(s[4]), "wall_s": wall, "clocks": clocks}
 
-    dev_t = timed_loop(False, args.steps, args.warmup)
+    eager_t = timed_loop(False, args.steps, args.warmup)  # stage breakdown (events between the stages)
+    dev_t = timed_loop(False, args.steps, args.warmup, graph=True) if graphed.get(False) else eager_t
+    for key in ("k1_ms", "gather_ms", "k2_ms"):
+        dev_t[key] = eager_t[key]
 
     # kernel-only timing of the dominant kernel (K1 hash) and of K2, alone on the stream
     def time_kernel(fn, reps: int) -> float:
@@ -415,7 +420,28 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world), reps)
     counts_host = table.counts.cpu().numpy()[multi_gpu.real_rows(n, world)].astype(np.int64)
 
-    e2e_t = timed_loop(True, max(2, args.steps // 2), 3) if do_e2e else None
+    # ---- result checksums (outside every timed region): must be identical for every --gpus N
+    real = torch.from_numpy(multi_gpu.real_rows(n, world)).to(dev)
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    ov_ck = torch.zeros(1, dtype=torch.int64, device=dev)
+    for r0 in range(0, n, 1024):  # row blocks keep the int64 temporaries small at 10,000 genomes
+        blk = result["ov"][real[r0: r0 + 1024]][:, real].to(torch.int64)
+        w = (idx[r0: r0 + 1024, None] * 1000003 + idx[None, :] * 7919 + 1) % 2147483647
+        ov_ck += (blk * w).sum()
+    if world > 1:
+        dist.all_reduce(ov_ck, op=dist.ReduceOp.SUM)  # the ranks hold disjoint parts of the matrix
+    rows_real = table.rows[real]
+    valid = torch.arange(rows_real.shape[1], device=dev)[None, :] < table.counts[real][:, None]
+    hash_ck = int((rows_real * valid).sum().item())  # wrapping int64 sum of every sketch hash
+    checksum = {"ov_weighted_sum": int(ov_ck.item()), "hash_sum": hash_ck, "sketch_total": int(counts_host.sum())}
+    del rows_real, valid
+
+    e2e_t = None
+    if do_e2e:
+        e2e_eager = timed_loop(True, max(2, args.steps // 2), 3)
+        e2e_t = timed_loop(True, max(2, args.steps // 2), 3, graph=True) if graphed.get(True) else e2e_eager
+        for key in ("k1_ms", "gather_ms", "k2_ms"):
+            e2e_t[key] = e2e_eager[key]
 
     if rank != 0:
         if world > 1:
@@ -476,8 +502,14 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                 {"value": None, "unit": UNIT, "skipped": "ASCII stream larger than the 12 GB host staging limit "
                                                          "of bench.py (or --no-e2e)"}),
         "gpu_launches": dev_t["launches"],
+        "cuda_graph": {"device_step": bool(graphed.get(False)), "e2e_step": bool(graphed.get(True)),
+                       "eager_ms_per_step": eager_t["ms"],
+                       "eager_e2e_ms_per_step": e2e_eager["ms"] if do_e2e else None,
+                       "note": "value / e2e time one graph launch per step when captured; stage_ms come "
+                               "from an eager pass with events between the stages"},
         "clocks": dev_t["clocks"],
         "sketch_sizes": {"mean": float(counts_host.mean()), "max": int(counts_host.max())},
+        "result_checksum": checksum,
         "library": engine.library_version(),
     }
     print(json.dumps(line), flush=True)
@@ -494,6 +526,7 @@ def main() -> None:
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA graph replay)")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="multi-GPU: plain NCCL all-gather instead of the fused finalize + peer-memory scatter")
     args = ap.parse_args()

@@ -429,11 +429,14 @@ class Engine:
 
     # ------------------------------------------------------------------ stage 2: intersect
     def intersect(self, q: SketchTable, s: SketchTable | None = None, *, rank: int = 0, world: int = 1,
-                  n_cells: int = 0, seg_cap: int = 0, idx_buckets: int = 0, max_count: int | None = None):
+                  n_cells: int = 0, seg_cap: int = 0, idx_buckets: int = 0, max_count: int | None = None,
+                  check: bool = True):
         """uint32 intersection sizes as an int32 torch tensor [nq, ns] (device).
 
         ``s is None`` = all-vs-all within ``q`` (only q < s is computed, the result is mirrored and
-        the diagonal holds the sketch sizes).
+        the diagonal holds the sketch sizes).  ``check=False`` only enqueues (no device->host read, so
+        the call can be captured into a CUDA graph; needs ``max_count``): the caller reads
+        ``check_status()`` afterwards and re-plans itself on ``ST_SEGMENT_OVERFLOW``.
         """
         torch = self.torch
         symmetric = s is None
@@ -448,6 +451,9 @@ class Engine:
             return ov
         mh = max_hash(q.scaled)
         if max_count is None:
+            if not check:
+                msg = "intersect(check=False) needs max_count (no device read is allowed)"
+                raise ValueError(msg)
             max_count = int(torch.maximum(q.counts.max(), s.counts.max()).item())
         cells = n_cells
         while True:
@@ -458,6 +464,8 @@ class Engine:
                 s.rows.data_ptr(), s.counts.data_ptr(), s.stride, ns,
                 1 if symmetric else 0, mh, max_count, cells, seg_cap, idx_buckets,
                 fence.data_ptr(), ov.data_ptr(), ns, rank, world, self.status.data_ptr(), self._stream()))
+            if not check:
+                return ov
             st = self._read_status()
             if st & ST_BUCKET_OVERFLOW:
                 msg = "a sketch bucket overflowed in an earlier sketch call whose status was not checked"

@@ -51,6 +51,25 @@ for mode in modes:
     whole = multi_gpu.combine_partial(part.clone(), world)
     results[mode] = (table.to_host(), whole.cpu().numpy(), int((part != 0).sum().item()))
 
+# the same step through pipeline.SourmashStep, eagerly and as a replayed CUDA graph
+from pyani_plus_b200 import pipeline  # noqa: E402
+
+tab = eng.alloc_table(plan)
+stepper = pipeline.SourmashStep(eng, plan, bufs, tab, K, world=world, rank=rank,
+                                gather=fused if int(ok.item()) else None)
+out = stepper.run()
+results["step_eager"] = (out["table"].to_host(), multi_gpu.combine_partial(out["ov"].clone(), world).cpu().numpy(),
+                         int((out["ov"] != 0).sum().item()))
+captured = torch.tensor([1 if stepper.capture() else 0], device=eng.device)
+dist.all_reduce(captured, op=dist.ReduceOp.MIN)
+if int(captured.item()):
+    for _ in range(3):
+        out = stepper.replay()
+        stepper.finish()
+    results["step_graph"] = (out["table"].to_host(),
+                             multi_gpu.combine_partial(out["ov"].clone(), world).cpu().numpy(),
+                             int((out["ov"] != 0).sum().item()))
+
 if rank == 0:
     full, full_off = eng.synth_ascii_stream(SEED, 0, N, LENGTH)
     ref = eng.sketch_ascii_stream(full, full_off, K, SCALED, from_host=False)

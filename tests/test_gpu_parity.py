@@ -317,3 +317,55 @@ def test_edge_shapes_vs_oracle(eng) -> None:
     ident, cov = engine.ani_host(ov.astype(np.uint32), counts, counts, k)
     assert np.isnan(ident[4, 4]) and np.isnan(ident[6, 6])  # empty sketches: no self row
     assert ident[0, 0] == 1.0 and ident[0, 1] == ident[1, 0] and cov[1, 0] >= cov[0, 1]
+
+
+def test_step_pipeline_eager_and_graph(eng) -> None:
+    """pipeline.SourmashStep (K1 -> finalize -> K2 -> ANI with no read-back in between): the eager step,
+    the replayed CUDA graph and the host-input (H2D inside) form give the oracle's sketches and counts."""
+    import torch
+
+    from pyani_plus_b200 import pipeline
+
+    n, length, k, scaled = 12, 400_000, 31, 200
+    d_ascii, tile_off = eng.synth_ascii_stream(SEED, 40, n, length)
+    plan = eng.plan_stream(tile_off, scaled)
+    bufs = eng.alloc_stream_buffers(plan, ascii_too=True)
+    tab = eng.alloc_table(plan)
+    eng.pack(d_ascii, plan, bufs)
+    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True)
+    h_ascii.copy_(d_ascii)
+    want_h, want_c = oracle.synth_sketch_batch(SEED, 40, n, length, k, scaled)
+    want_ov = oracle.intersect_all(want_h, want_c)
+    stepper = pipeline.SourmashStep(eng, plan, bufs, tab, k, h_ascii=h_ascii)
+
+    def check(out: dict) -> None:
+        got = out["table"].to_host()
+        for g in range(n):
+            assert got[g].tolist() == want_h[g, : want_c[g]].tolist(), g
+        assert (out["ov"].cpu().numpy().astype(np.int64) == want_ov).all()
+
+    check(stepper.run())
+    out = stepper.run(from_host=True, to_host=True)
+    check(out)
+    ident_eager = out["identity_host"].clone()
+    for from_host in (False, True):
+        assert stepper.capture(from_host=from_host, to_host=from_host)
+        tab["table"].fill_(7)  # stale rows must be overwritten by the replay
+        for _ in range(2):
+            out = stepper.replay(from_host=from_host, to_host=from_host)
+            stepper.finish()
+        check(out)
+    np.testing.assert_array_equal(out["identity_host"].numpy(), ident_eager.numpy())
+    ident, _ = engine_ani_host(out["ov"], out["table"], k)
+    np.testing.assert_allclose(out["identity_host"].numpy(), ident, rtol=0, atol=ANI_ATOL, equal_nan=True)
+    # a size hint that is too small is reported, not silently truncated
+    small = pipeline.SourmashStep(eng, plan, bufs, tab, k, size_hint=100)
+    with pytest.raises(Exception, match="size_hint"):
+        small.run()
+
+
+def engine_ani_host(ov, table, k: int):
+    from pyani_plus_b200 import engine
+
+    counts = table.counts.cpu().numpy()
+    return engine.ani_host(ov.cpu().numpy().astype(np.uint32), counts, counts, k)
