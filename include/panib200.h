@@ -65,7 +65,9 @@ extern "C" {
 #define PANIB_E_NODEVICE (-3)      /* no CUDA device: this library has no CPU path                  */
 
 /* d_status is int32[4], zero-initialised by the caller: [0] = PANIB_ST_* bits OR-ed in by kernels,
- * [1] = largest sketch size seen by the finalize kernel (atomicMax), [2..3] reserved.
+ * [1] = largest sketch size seen by the finalize kernel (atomicMax), [2] = scratch of the sketch kernel
+ * (ticket counter of its dynamic tile schedule; zeroed by the library before each launch, so one status
+ * block must not be shared by sketch calls running concurrently on different streams), [3] reserved.
  * The finalize kernel also stores each row's size in the row's LAST slot (row[row_stride-1]), so a
  * single all-gather of the rows carries the sizes along. */
 #define PANIB_ST_BUCKET_OVERFLOW 1 /* a sketch bucket filled up: re-run with more buckets           */

@@ -114,7 +114,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
                    const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
                    uint32_t seed, uint64_t max_hash, const int32_t *__restrict__ nb,
                    const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
-                   int32_t *flags, int32_t *status) {
+                   int32_t *flags, int32_t *status, uint32_t *ticket) {
     // stream tiles [tile_begin, n_tiles) = CTA tiles [tile_begin*S, n_tiles*S), S = kTileBases/kCtaTile:
     // persistent CTAs, double buffer, two barriers per CTA tile
     __shared__ __align__(16) uint32_t sp[2][kTileWords];
@@ -136,11 +136,22 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         cp_async_commit();
     };
     prefetch(tile, 0);
+    // Tiles after a CTA's first come from a ticket counter (`ticket`, zeroed by the host before the
+    // launch) rather than from a fixed stride: the warp scheduler favours some resident CTAs, so with
+    // equal fixed shares the favoured CTAs leave early and the SM ends the launch under-occupied
+    // (ncu: 24 of 32 warps active on average).  Thread 0 draws the ticket for the tile after next while
+    // the current tile is hashed; the barrier that ends the tile publishes it.
+    __shared__ int64_t s_next;
+    const int64_t dyn_base = tile_begin * S + gridDim.x;
+    if (ticket) {
+        if (threadIdx.x == 0) s_next = dyn_base + atomicAdd(ticket, 1u);
+        __syncthreads();
+    }
+    int64_t next = ticket ? s_next : tile + gridDim.x;
     const int u = threadIdx.x >> 2, a = threadIdx.x & 3;
     int g = 0;
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; tile < n_tiles; ++it) {
         const int cur = it & 1;
-        const int64_t next = tile + gridDim.x;
         if (next < n_tiles) {
             prefetch(next, cur ^ 1);
             cp_async_wait<1>();
@@ -148,6 +159,8 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
             cp_async_wait<0>();
         }
         __syncthreads();
+        uint32_t drawn = 0;
+        if (ticket && threadIdx.x == 0 && next < n_tiles) drawn = atomicAdd(ticket, 1u);
         const uint32_t m = threadIdx.x < kTileMaskWords ? sm[cur][threadIdx.x] : 0u;
         const bool dirty = __syncthreads_or(m != 0u) != 0;
         g = find_genome(tile_off, n_genomes, tile / S, g);
@@ -158,7 +171,10 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         } else {
             hash_thread_kmers<K, true>(sp[cur], sm[cur], blk, kThreadsK1, u, a, seed, emit);
         }
+        if (ticket && threadIdx.x == 0) s_next = next < n_tiles ? dyn_base + drawn : n_tiles;
         __syncthreads();
+        tile = next;
+        next = ticket ? s_next : next + gridDim.x;
     }
 }
 
@@ -423,10 +439,19 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
                              int64_t row_stride, int32_t *d_flags, int32_t *d_status, cudaStream_t st) {
     const int64_t n = tile_end - tile_begin;
     if (n <= 0) return PANIB_OK;
+    // ticket counter of the dynamic tile schedule: word 2 of the caller's status block (one engine =
+    // one stream), zeroed in stream order before every launch; without a status block, fixed strides
+    uint32_t *ticket = nullptr;
+#ifndef PANIB_K1_STATIC_TILES
+    if (d_status && (k == 21 || k == 31) && n * (kTileBases / kCtaTile) < 0xF0000000LL) {
+        ticket = reinterpret_cast<uint32_t *>(d_status) + 2;
+        PANIB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st));
+    }
+#endif
 #define PANIB_LAUNCH_K(KK)                                                                                   \
-    sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, kK1DynSmem, st>>>(                                    \
+    sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, kK1DynSmem, st>>>( \
         d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, seed, max_hash, d_nb, d_bmul,    \
-        d_table, row_stride, d_flags, d_status)
+        d_table, row_stride, d_flags, d_status, ticket)
     switch (k) {
     case 21: PANIB_LAUNCH_K(21); break;
     case 31: PANIB_LAUNCH_K(31); break;
