@@ -301,7 +301,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     from pyani_plus_b200 import pipeline
 
     stepper = pipeline.SourmashStep(eng, plan, bufs, tab, k, world=world, rank=rank, gather=fused,
-                                    size_hint=size_hint, h_ascii=h_ascii)
+                                    size_hint=size_hint, h_ascii=h_ascii, k2_method=args.k2)
     # the step as ONE CUDA graph launch (all ranks must agree, the gather has barriers inside)
     graphed: dict = {}
     per_step_launches: dict = {}
@@ -417,7 +417,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     finalize_only()
     step(False)
     table = result["table"]
-    k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world), reps)
+    k2_ms = time_kernel(lambda: eng.intersect(table, rank=rank, world=world, max_count=size_hint, check=False,
+                                              method=stepper.k2_method), reps)
+    assert eng.check_status() == 0
     counts_host = table.counts.cpu().numpy()[multi_gpu.real_rows(n, world)].astype(np.int64)
 
     # ---- result checksums (outside every timed region): must be identical for every --gpus N
@@ -467,7 +469,8 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                "ms_per_launch": k1_hash_ms, "bytes_per_bp": 0.25 + 0.125 + 8.0 / scaled,
                "note": "integer-ALU bound by construction (MurmurHash3 over 31 ASCII bytes per base); see "
                        "DESIGN.md and profiles/ for pipe utilisation"}
-    roof_k2 = {"kernel": "intersect_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+    roof_k2 = {"kernel": ("intersect_kernel (K2, probing form)" if stepper.k2_method == "probe" else
+                          "index_* kernels (K2, inverted-index form: sort + AND/POPC bit matrix + rare-pair adds)"), "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                "frac": k2_gbs / peak,
                "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k2")) if world == 1 else None,
                "algorithmic_bytes": k2_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
@@ -502,6 +505,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                 {"value": None, "unit": UNIT, "skipped": "ASCII stream larger than the 12 GB host staging limit "
                                                          "of bench.py (or --no-e2e)"}),
         "gpu_launches": dev_t["launches"],
+        "k2_method": {"used": stepper.k2_method, "requested": args.k2, "estimates": eng.last_intersect_estimates},
         "cuda_graph": {"device_step": bool(graphed.get(False)), "e2e_step": bool(graphed.get(True)),
                        "eager_ms_per_step": eager_t["ms"],
                        "eager_e2e_ms_per_step": e2e_eager["ms"] if do_e2e else None,
@@ -526,6 +530,8 @@ def main() -> None:
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--k2", default="auto", choices=["auto", "probe", "index"],
+                    help="pairwise kernel: probing form, inverted-index form, or chosen from the data")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA graph replay)")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="multi-GPU: plain NCCL all-gather instead of the fused finalize + peer-memory scatter")

@@ -318,6 +318,38 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, uint32_t
         }
     }
 
+#if defined(PANIB_K1_ROLLED)
+    // Rolled form (experiment, not the default): 4 groups of 4 k-mers; between groups the packed
+    // windows slide by one word so that the group body uses fixed register indices.  4x smaller code,
+    // 48 registers; measured no faster than the unrolled form.
+    static_assert(kKmersPerThread == 16 && NX >= 6, "rolled loop assumes 16 k-mers per thread");
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int j = 4 * g + jj;
+            bool valid = true;
+            if (DIRTY) {
+                const int pos = 4 * kKmersPerThread * u + a + 4 * j;
+                uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
+                if (K < 32) mw &= (1u << (K & 31)) - 1u;
+                valid = (mw == 0u);
+            }
+            const uint64_t F = window<K, NX>(X, 8 * jj);         // X slid down by g words
+            const uint64_t R = window<K, NX>(Xr, 8 * (15 - jj));  // Xr slid up by g words
+            const uint32_t *words = F < R ? fw + j * blk_stride : rv + (kKmersPerThread - 1 - j) * blk_stride;
+            uint32_t W[NWD];
+#pragma unroll
+            for (int i = 0; i < NWD; i++) W[i] = words[i * blk_stride];
+            const uint64_t h = murmur_words<K>(W, seed);
+            if (!DIRTY || valid) emit(h);
+        }
+#pragma unroll
+        for (int w = 0; w < NX - 1; w++) X[w] = X[w + 1];
+#pragma unroll
+        for (int w = NX - 1; w > 0; w--) Xr[w] = Xr[w - 1];
+    }
+#else
 #pragma unroll
     for (int j = 0; j < kKmersPerThread; j++) {
         bool valid = true;
@@ -336,6 +368,7 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, uint32_t
         const uint64_t h = murmur_words<K>(W, seed);
         if (!DIRTY || valid) emit(h);
     }
+#endif
 }
 
 }  // namespace panib

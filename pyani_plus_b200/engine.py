@@ -87,6 +87,12 @@ def load_library() -> ctypes.CDLL:
                                   _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp]
     L.panib_intersect_fence_entries.restype = _i64
     L.panib_intersect_fence_entries.argtypes = [_i64, _i64, _u64, _i64, _i32, _i32]
+    L.panib_index_workspace_bytes.restype = _i32
+    L.panib_index_workspace_bytes.argtypes = [_i64, _i64, _i32, ctypes.POINTER(_i64)]
+    L.panib_index_build.restype = _i32
+    L.panib_index_build.argtypes = [_vp, _vp, _i64, _i64, _u64, _i64, _i32, _vp, _i64, _vp, _vp, _vp]
+    L.panib_index_count.restype = _i32
+    L.panib_index_count.argtypes = [_vp, _i64, _u64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]
     L.panib_ani_device.restype = _i32
     L.panib_ani_device.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]
     L.panib_ani_host.restype = _i32
@@ -226,6 +232,8 @@ class Engine:
         torch.cuda.set_device(self.device)
         self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.last_max_count = 0
+        self.last_intersect_method = ""
+        self.last_intersect_estimates: dict = {}
         self.max_batch_bytes = 1 << 31  # ASCII bytes staged per sketch batch
 
     # ------------------------------------------------------------------ helpers
@@ -430,14 +438,24 @@ class Engine:
     # ------------------------------------------------------------------ stage 2: intersect
     def intersect(self, q: SketchTable, s: SketchTable | None = None, *, rank: int = 0, world: int = 1,
                   n_cells: int = 0, seg_cap: int = 0, idx_buckets: int = 0, max_count: int | None = None,
-                  check: bool = True):
+                  check: bool = True, method: str = "auto", tau: int = 0):
         """uint32 intersection sizes as an int32 torch tensor [nq, ns] (device).
 
         ``s is None`` = all-vs-all within ``q`` (only q < s is computed, the result is mirrored and
         the diagonal holds the sketch sizes).  ``check=False`` only enqueues (no device->host read, so
         the call can be captured into a CUDA graph; needs ``max_count``): the caller reads
         ``check_status()`` afterwards and re-plans itself on ``ST_SEGMENT_OVERFLOW``.
+
+        ``method``: ``"probe"`` = the shared-memory probing kernel (cost ~ pairs x sketch size, any
+        shape), ``"index"`` = the inverted-index form (sort by hash, bit matrix for frequent hashes,
+        pair expansion for rare ones; cost ~ what the genomes share; all-vs-all only), ``"auto"`` =
+        build the index when the probing estimate is not negligible and take the cheaper of the two
+        from the index statistics (one small device->host read; with ``check=False`` auto means
+        probe).  The counts are identical; ``last_intersect_method`` tells which one ran.
         """
+        if method not in ("auto", "probe", "index"):
+            msg = f"unknown intersect method {method!r}"
+            raise ValueError(msg)
         torch = self.torch
         symmetric = s is None
         if symmetric:
@@ -455,6 +473,17 @@ class Engine:
                 msg = "intersect(check=False) needs max_count (no device read is allowed)"
                 raise ValueError(msg)
             max_count = int(torch.maximum(q.counts.max(), s.counts.max()).item())
+        indexable = symmetric and nq >= 2 and mh < (1 << 64) - 16 and nq * max(1, max_count) < (1 << 31) - 512
+        if method == "index" and not indexable:
+            msg = "intersect(method='index') needs an all-vs-all call with n * max_count < 2^31 and scaled >= 2"
+            raise ValueError(msg)
+        if method == "auto" and (not indexable or not check):
+            method = "probe"
+        if method != "probe":
+            done = self._intersect_indexed(q, ov, mh, max_count, tau, rank, world, check, method == "auto")
+            if done is not None:
+                return done
+        self.last_intersect_method = "probe"
         cells = n_cells
         while True:
             nfence = int(self.lib.panib_intersect_fence_entries(nq, ns, mh, max_count, cells, seg_cap))
@@ -474,6 +503,62 @@ class Engine:
                 cells = max(2, cells * 2) if cells else max(2, 2 * -(-max_count // 4096))
                 if cells > 1 << 16:
                     msg = "pairwise segments keep overflowing"
+                    raise EngineError(msg)
+                continue
+            return ov
+
+    # cost model of Engine.intersect(method="auto"), seconds per unit on one B200 (measured)
+    COST_PROBE_PER_ELEMENT = 0.6e-12   # probing kernel: per pair and per sketch element (both sketches)
+    COST_INDEX_PER_ENTRY = 1.2e-10     # flatten + radix sort + run detection, per (hash, genome) entry
+    COST_INDEX_PER_WORD = 0.8e-12      # AND+POPC kernel: per pair and per 32 bit-matrix columns
+    COST_INDEX_PER_RARE_PAIR = 2.0e-11 # atomicAdd expansion of the rare hashes, per pair
+
+    def _intersect_indexed(self, q: SketchTable, ov, mh: int, max_count: int, tau: int, rank: int, world: int,  # noqa: ANN001, PLR0913
+                           check: bool, auto: bool):  # noqa: ANN202
+        """Inverted-index form of the all-vs-all intersection (csrc/index.cu).  Returns ``ov``, or None
+        when ``auto`` decided that the probing kernel is cheaper for this data."""
+        torch = self.torch
+        n = q.n
+        pairs = n * (n - 1) / 2 / world
+        est_probe = pairs * 2 * max_count * self.COST_PROBE_PER_ELEMENT
+        if auto and est_probe < 3e-4:  # the index has ~10 launches of fixed cost: not worth it
+            return None
+        while True:
+            cap = max(1, int(max_count))
+            tau_ = tau if tau >= 2 else max(8, n // 32)
+            need = _i64(0)
+            _check(self.lib.panib_index_workspace_bytes(n, cap, tau_, ctypes.byref(need)))
+            work = getattr(self, "_index_work", None)
+            if work is None or work.numel() < need.value:
+                self._index_work = work = None  # free the old one first
+                self._index_work = work = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+                self._index_stats = torch.zeros(4, dtype=torch.int64, device=self.device)
+            stats = self._index_stats
+            _check(self.lib.panib_index_build(q.rows.data_ptr(), q.counts.data_ptr(), q.stride, n, mh, cap, tau_,
+                                              work.data_ptr(), work.numel(), stats.data_ptr(),
+                                              self.status.data_ptr(), self._stream()))
+            if auto:
+                n_dense, rare_pairs, _, _ = stats.tolist()
+                est_index = (n * cap * self.COST_INDEX_PER_ENTRY + pairs * -(-n_dense // 32) * self.COST_INDEX_PER_WORD
+                             + rare_pairs / world * self.COST_INDEX_PER_RARE_PAIR)
+                self.last_intersect_estimates = {"probe_s": est_probe, "index_s": est_index,
+                                                 "frequent_hashes": n_dense, "rare_pairs": rare_pairs}
+                if est_index >= est_probe:
+                    return None
+            _check(self.lib.panib_index_count(q.counts.data_ptr(), n, mh, cap, tau_, work.data_ptr(), work.numel(),
+                                              stats.data_ptr(), ov.data_ptr(), q.n, rank, world,
+                                              self.status.data_ptr(), self._stream()))
+            self.last_intersect_method = "index"
+            if not check:
+                return ov
+            st = self._read_status()
+            if st & ST_BUCKET_OVERFLOW:
+                msg = "a sketch bucket overflowed in an earlier sketch call whose status was not checked"
+                raise EngineError(msg)
+            if st & ST_SEGMENT_OVERFLOW:  # a sketch is larger than cap: take the real maximum and redo
+                max_count = int(q.counts.max().item())
+                if max_count <= cap:
+                    msg = "index intersect keeps overflowing"
                     raise EngineError(msg)
                 continue
             return ov

@@ -21,9 +21,12 @@ class SourmashStep:
     """One pass of the hot path for a planned stream on this rank."""
 
     def __init__(self, eng, plan, bufs: dict, tab: dict, k: int, *, world: int = 1, rank: int = 0,  # noqa: ANN001, PLR0913
-                 gather=None, size_hint: int | None = None, h_ascii=None) -> None:  # noqa: ANN001
+                 gather=None, size_hint: int | None = None, h_ascii=None, k2_method: str = "auto") -> None:  # noqa: ANN001
         """``gather`` is a ``multi_gpu.SymmetricGather`` (fused finalize + all-gather) or None (NCCL
-        all-gather when ``world > 1``); ``h_ascii`` the pinned ASCII stream for host-input steps."""
+        all-gather when ``world > 1``); ``h_ascii`` the pinned ASCII stream for host-input steps;
+        ``k2_method`` as in ``Engine.intersect`` -- ``"auto"`` is resolved ONCE, on the first step, from
+        that step's data (one extra checked intersect), and then kept (a captured graph cannot branch)."""
+        self.k2_method = k2_method
         self.eng, self.plan, self.bufs, self.tab, self.k = eng, plan, bufs, tab, k
         self.world, self.rank, self.gather = world, rank, gather
         self.size_hint = plan.sketch_size_hint() if size_hint is None else size_hint
@@ -61,8 +64,18 @@ class SourmashStep:
         table = _engine.SketchTable(all_rows, all_counts, k, plan.scaled)
         if marks is not None:
             marks[1].record()
+        if self.k2_method == "auto":  # first step only: let the engine choose from this data, then stick to it
+            eng.intersect(table, rank=self.rank, world=self.world, max_count=self.size_hint, method="auto")
+            self.k2_method = eng.last_intersect_method
+            if self.world > 1:  # all ranks must take the same path (their partial matrices are summed)
+                import torch.distributed as dist  # noqa: PLC0415
+
+                flag = eng.torch.tensor([1 if self.k2_method == "index" else 0], device=eng.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                self.k2_method = "index" if int(flag.item()) else "probe"
         # K2's shared memory is sized from the genome lengths (the kernel verifies it): no read-back
-        ov = eng.intersect(table, rank=self.rank, world=self.world, max_count=self.size_hint, check=False)
+        ov = eng.intersect(table, rank=self.rank, world=self.world, max_count=self.size_hint, check=False,
+                           method=self.k2_method)
         if marks is not None:
             marks[2].record()
         ident, cov = eng.ani_device(ov, table)

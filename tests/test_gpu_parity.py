@@ -369,3 +369,62 @@ def engine_ani_host(ov, table, k: int):
 
     counts = table.counts.cpu().numpy()
     return engine.ani_host(ov.cpu().numpy().astype(np.uint32), counts, counts, k)
+
+
+def _pool_sketches(rng, n: int, pool: int, lo: int, hi: int) -> list[np.ndarray]:
+    """n sketches drawn from a shared pool of hashes (so that hashes are shared by 1..n genomes)."""
+    universe = np.unique(rng.integers(1, 1 << 53, pool, dtype=np.uint64))
+    weights = rng.random(len(universe)) ** 3  # a few very frequent hashes, many rare ones
+    weights /= weights.sum()
+    out = []
+    for _ in range(n):
+        size = int(rng.integers(lo, hi + 1))
+        out.append(np.sort(rng.choice(universe, size=min(size, len(universe)), replace=False, p=weights)))
+    return out
+
+
+@pytest.mark.parametrize("tau", [2, 5, 0, 100000])
+def test_intersect_index_form_equals_probe_and_oracle(eng, tau: int) -> None:
+    """The inverted-index form of K2 (sort + bit matrix + rare-pair adds) gives the probing kernel's and
+    the oracle's counts: all runs frequent (tau=2), mixed, the default, all runs rare (huge tau); with
+    empty sketches, identical sketches, single-hash sketches; and sharded over 3 ranks."""
+    rng = np.random.default_rng(7 + tau)
+    sk = _pool_sketches(rng, 70, 6000, 0, 900)
+    sk[3] = np.zeros(0, dtype=np.uint64)
+    sk[10] = sk[11].copy()  # identical genomes
+    sk[20] = sk[21][:1].copy()
+    sk.append(np.array([5, 9, (1 << 53) + 12345], dtype=np.uint64))
+    table = eng.table_from_host(sk, 31, 1000)
+    n = len(sk)
+    want = np.zeros((n, n), dtype=np.int64)
+    for i in range(n):
+        for j in range(n):
+            want[i, j] = len(np.intersect1d(sk[i], sk[j], assume_unique=True))
+    probe = eng.intersect(table, method="probe").cpu().numpy().astype(np.int64)
+    assert (probe == want).all()
+    got = eng.intersect(table, method="index", tau=tau).cpu().numpy().astype(np.int64)
+    assert eng.last_intersect_method == "index"
+    assert (got == want).all(), np.argwhere(got != want)[:5]
+    # too small a capacity hint is detected and redone with the real maximum
+    again = eng.intersect(table, method="index", tau=tau, max_count=50).cpu().numpy().astype(np.int64)
+    assert (again == want).all()
+    parts = sum(eng.intersect(table, method="index", tau=tau, rank=r, world=3).cpu().numpy().astype(np.int64)
+                for r in range(3))
+    assert (parts == want).all()
+
+
+def test_intersect_auto_picks_a_method_and_matches(eng) -> None:
+    """method="auto" on a family large enough for the index to be considered: same counts either way."""
+    n, length, k, scaled = 150, 600_000, 31, 100
+    d_ascii, tile_off = eng.synth_ascii_stream(SEED, 300, n, length)
+    table = eng.sketch_ascii_stream(d_ascii, tile_off, k, scaled, from_host=False)
+    del d_ascii
+    probe = eng.intersect(table, method="probe").cpu().numpy()
+    auto = eng.intersect(table).cpu().numpy()
+    assert eng.last_intersect_method in ("probe", "index")
+    index = eng.intersect(table, method="index").cpu().numpy()
+    assert (auto == probe).all() and (index == probe).all()
+    assert (np.diag(index) == table.counts.cpu().numpy()).all()
+    # rectangular calls cannot use the index
+    with pytest.raises(ValueError, match="all-vs-all"):
+        eng.intersect(table, table, method="index")

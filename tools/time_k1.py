@@ -47,8 +47,19 @@ assert eng.check_status() == 0
 table = engine.SketchTable(tab["table"], tab["counts"], k, scaled)
 chk = int(table.counts.sum().item())
 mc = int(length / scaled * 1.3) + 64
-t_k2 = timeit(lambda: eng.intersect(table))
-ov = eng.intersect(table)
+real_max = int(table.counts.max().item())
+t_k2 = timeit(lambda: eng.intersect(table, method="probe", check=False, max_count=real_max))
+ov = eng.intersect(table, method="probe")
+idx_note = ""
+try:
+    t_idx = timeit(lambda: eng.intersect(table, method="index", check=False, max_count=real_max))
+    ov_idx = eng.intersect(table, method="index")
+    same = bool((ov_idx == ov).all().item())
+    eng.intersect(table, method="auto")
+    idx_note = (f" | K2 index {t_idx[0]:.3f} ms = {n*(n-1)/2/t_idx[0]/1e3:.2f} Mpairs/s equal={same} "
+                f"auto->{eng.last_intersect_method} est={eng.last_intersect_estimates}")
+except Exception as exc:  # noqa: BLE001
+    idx_note = f" | K2 index failed: {exc}"
 print(f"{workload} hash {t_hash[0]:.3f} ms (min {t_hash[1]:.3f}) = {n*length/t_hash[0]/1e6:.1f} Gbp/s | "
       f"finalize {t_fin[0]:.3f} ms | K2 {t_k2[0]:.3f} ms = {n*(n-1)/2/t_k2[0]/1e3:.2f} Mpairs/s | "
-      f"sum(counts)={chk} sum(ov)={int(ov.to(torch.int64).sum().item())}")
+      f"sum(counts)={chk} sum(ov)={int(ov.to(torch.int64).sum().item())}{idx_note}")
