@@ -17,13 +17,15 @@ from tools.parity_at_scale import check_workload
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize(("workload", "sample"), [("config3", 0), ("config5", 208), ("config4", 256)])
-def test_baseline_config_against_oracle(workload: str, sample: int) -> None:
+@pytest.mark.parametrize(("workload", "sample", "k2"), [("config3", 0, "probe"), ("config3", 0, "index"),
+                                                        ("config5", 208, "auto"), ("config4", 256, "auto")])
+def test_baseline_config_against_oracle(workload: str, sample: int, k2: str) -> None:
     import torch
 
     if workload == "config4" and torch.cuda.mem_get_info(0)[1] < 60 << 30:
         pytest.skip("needs a 64 GB+ GPU")
-    report = check_workload(workload, sample)
+    report = check_workload(workload, sample, k2_method=k2)
+    assert k2 == "auto" or report["k2_method"] == k2
     assert report["sketches_with_mismatch"] == 0, report
     assert report["count_cells_with_mismatch"] == 0, report
     assert report["ani_device_vs_host_max_abs_err"] <= 1e-12, report

@@ -30,7 +30,7 @@ from bench import SEED, WORKLOADS  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 
-def check_workload(workload: str, sample: int = 0, batch: int = 250) -> dict:
+def check_workload(workload: str, sample: int = 0, batch: int = 250, k2_method: str = "auto") -> dict:
     """Run one BASELINE workload on cuda:0, check it against the oracle, return the report dict."""
     import torch
 
@@ -47,7 +47,8 @@ def check_workload(workload: str, sample: int = 0, batch: int = 250) -> dict:
         del d_ascii
     table = parts[0] if len(parts) == 1 else eng.concat_tables(parts, k, scaled)
     del parts
-    ov_d = eng.intersect(table)
+    ov_d = eng.intersect(table, method=k2_method)
+    k2_used = eng.last_intersect_method
     ident_d, cov_d = eng.ani_device(ov_d, table)
     torch.cuda.synchronize()
     gpu_s = time.perf_counter() - t0
@@ -129,7 +130,7 @@ def check_workload(workload: str, sample: int = 0, batch: int = 250) -> dict:
         "ani_host_rows_not_equal_oracle": row_mismatch, "whole_matrix": props,
         "sketch_sizes": {"min": int(counts.min()), "mean": float(counts.mean()), "max": int(counts.max())},
         "seconds": {"gpu_generate_sketch_intersect": gpu_s, "oracle_sketch": sketch_s, "oracle_intersect": inter_s},
-        "oracle_threads": oracle.num_threads(), "library": engine.library_version(), "ok": ok}
+        "k2_method": k2_used, "oracle_threads": oracle.num_threads(), "library": engine.library_version(), "ok": ok}
 
 
 def main() -> None:
@@ -137,8 +138,9 @@ def main() -> None:
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--sample", type=int, default=0, help="genomes checked by the oracle (0 = all)")
     ap.add_argument("--batch", type=int, default=250, help="genomes generated + sketched per GPU pass")
+    ap.add_argument("--k2", default="auto", choices=["auto", "probe", "index"])
     args = ap.parse_args()
-    report = check_workload(args.workload, args.sample, args.batch)
+    report = check_workload(args.workload, args.sample, args.batch, args.k2)
     print(json.dumps(report), flush=True)
     sys.exit(0 if report["ok"] else 1)
 

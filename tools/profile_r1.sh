@@ -23,4 +23,10 @@ ncu --set full --clock-control none --import-source on -k regex:intersect_kernel
 # 3) K2 where it matters: 1,000 genomes (config 3), 499,500 pairs in one launch
 ncu --set full --clock-control none --import-source on -k regex:intersect_kernel -s 1 -c 1 \
     -f -o $OUT/prof_k2c3_$TAG python tools/time_k1.py config3 1 > $OUT/prof_k2c3_$TAG.log 2>&1
+# 4) K2, inverted-index form at config 3: every launch with its time (sort / scan / index_* kernels), and a
+#    full capture of the AND+POPC bit-matrix kernel
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file $OUT/launches_idx_$TAG.csv python tools/time_k1.py config3 1 > $OUT/launches_idx_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:index_dense_kernel -s 1 -c 1 \
+    -f -o $OUT/prof_k2idx_$TAG python tools/time_k1.py config3 1 > $OUT/prof_k2idx_$TAG.log 2>&1
 ls -la $OUT | grep $TAG

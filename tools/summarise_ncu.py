@@ -19,6 +19,9 @@ KEYS = [
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__waves_per_multiprocessor",
     "sm__warps_active.avg.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "smsp__thread_inst_executed_per_inst_executed.ratio",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
@@ -98,9 +101,15 @@ def main() -> None:
     launches = OUT / f"launches_{tag}.csv"
     if launches.is_file():
         (PROF / f"{tag}_launches.md").write_text(summarise_launches(launches))
+    launches_idx = OUT / f"launches_idx_{tag}.csv"
+    if launches_idx.is_file():
+        (PROF / f"{tag}_launches_k2_index.md").write_text(
+            "`python tools/time_k1.py config3 1`: K1, the probing K2 and the inverted-index K2 (CUB radix sort + "
+            "scan + `index_*` kernels) on 1,000 genomes\n\n" + summarise_launches(launches_idx))
     for kind, title in (("k1", "K1 sketch_hash_kernel (config 2: 100 x 5 Mb)"),
                         ("k2", "K2 intersect_kernel (config 2: 4,950 pairs)"),
-                        ("k2c3", "K2 intersect_kernel (config 3: 1,000 genomes, 499,500 pairs)")):
+                        ("k2c3", "K2 intersect_kernel (config 3: 1,000 genomes, 499,500 pairs)"),
+                        ("k2idx", "K2 index_dense_kernel, AND+POPC over the bit matrix (config 3: 1,000 genomes)")):
         rep = OUT / f"prof_{kind}_{tag}.ncu-rep"
         if rep.is_file():
             (PROF / f"{tag}_{kind}_ncu.md").write_text(summarise_report(rep, title) + "\n")
