@@ -68,14 +68,21 @@ index_classify_kernel(const uint64_t *__restrict__ keys, const int32_t *__restri
                       const int32_t *__restrict__ gidx, int64_t total, uint64_t max_hash, int tau,
                       int32_t *__restrict__ densecol, unsigned long long *__restrict__ stats) {
     const int64_t r = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    if (r >= gidx[total - 1]) return;
-    const int s = start[r], m = start[r + 1] - s;
-    int col = -1;
-    if (keys[s] <= max_hash) {
-        if (m >= tau) col = (int)atomicAdd(stats + 0, 1ull);
-        else if (m >= 2) atomicAdd(stats + 1, (unsigned long long)m * (unsigned long long)(m - 1) / 2ull);
+    const bool live = r < gidx[total - 1];
+    unsigned long long pairs = 0ull;
+    if (live) {
+        const int s = start[r], m = start[r + 1] - s;
+        int col = -1;
+        if (keys[s] <= max_hash) {
+            if (m >= tau) col = (int)atomicAdd(stats + 0, 1ull);
+            else if (m >= 2) pairs = (unsigned long long)m * (unsigned long long)(m - 1) / 2ull;
+        }
+        densecol[r] = col;
     }
-    densecol[r] = col;
+    // one atomic per warp for the rare-pair total (millions of runs would otherwise queue on one address)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+    if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(stats + 1, pairs);
 }
 
 __global__ void __launch_bounds__(kIdxThreads)

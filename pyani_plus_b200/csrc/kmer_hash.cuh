@@ -318,57 +318,42 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, uint32_t
         }
     }
 
-#if defined(PANIB_K1_ROLLED)
-    // Rolled form (experiment, not the default): 4 groups of 4 k-mers; between groups the packed
-    // windows slide by one word so that the group body uses fixed register indices.  4x smaller code,
-    // 48 registers; measured no faster than the unrolled form.
-    static_assert(kKmersPerThread == 16 && NX >= 6, "rolled loop assumes 16 k-mers per thread");
-#pragma unroll 1
-    for (int g = 0; g < 4; g++) {
+    // PANIB_K1_GROUP k-mers are hashed back to back before any of them is offered to the table: the
+    // conditional insert (a call) ends a basic block, and inside one block the compiler can interleave
+    // the independent MurmurHash3 chains of the group.  Measured neutral on B200 (groups of 1/2/4/8:
+    // 2.68 / 2.68 / 2.71 / 2.68 ms at config 2 -- the kernel is bound by pipe throughput, not by
+    // dependency stalls), so the default stays 1.
+#ifndef PANIB_K1_GROUP
+#define PANIB_K1_GROUP 1
+#endif
+    constexpr int GRP = PANIB_K1_GROUP;
+    static_assert(kKmersPerThread % GRP == 0, "group size must divide the k-mers per thread");
 #pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-            const int j = 4 * g + jj;
-            bool valid = true;
+    for (int j0 = 0; j0 < kKmersPerThread; j0 += GRP) {
+        uint64_t h[GRP];
+        bool valid[GRP];
+#pragma unroll
+        for (int jj = 0; jj < GRP; jj++) {
+            const int j = j0 + jj;
+            valid[jj] = true;
             if (DIRTY) {
                 const int pos = 4 * kKmersPerThread * u + a + 4 * j;
                 uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
                 if (K < 32) mw &= (1u << (K & 31)) - 1u;
-                valid = (mw == 0u);
+                valid[jj] = (mw == 0u);
             }
-            const uint64_t F = window<K, NX>(X, 8 * jj);         // X slid down by g words
-            const uint64_t R = window<K, NX>(Xr, 8 * (15 - jj));  // Xr slid up by g words
+            const uint64_t F = window<K, NX>(X, 8 * j);
+            const uint64_t R = window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
             const uint32_t *words = F < R ? fw + j * blk_stride : rv + (kKmersPerThread - 1 - j) * blk_stride;
             uint32_t W[NWD];
 #pragma unroll
             for (int i = 0; i < NWD; i++) W[i] = words[i * blk_stride];
-            const uint64_t h = murmur_words<K>(W, seed);
-            if (!DIRTY || valid) emit(h);
+            h[jj] = murmur_words<K>(W, seed);
         }
 #pragma unroll
-        for (int w = 0; w < NX - 1; w++) X[w] = X[w + 1];
-#pragma unroll
-        for (int w = NX - 1; w > 0; w--) Xr[w] = Xr[w - 1];
+        for (int jj = 0; jj < GRP; jj++)
+            if (!DIRTY || valid[jj]) emit(h[jj]);
     }
-#else
-#pragma unroll
-    for (int j = 0; j < kKmersPerThread; j++) {
-        bool valid = true;
-        if (DIRTY) {
-            const int pos = 4 * kKmersPerThread * u + a + 4 * j;
-            uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
-            if (K < 32) mw &= (1u << (K & 31)) - 1u;
-            valid = (mw == 0u);
-        }
-        const uint64_t F = window<K, NX>(X, 8 * j);
-        const uint64_t R = window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
-        const uint32_t *words = F < R ? fw + j * blk_stride : rv + (kKmersPerThread - 1 - j) * blk_stride;
-        uint32_t W[NWD];
-#pragma unroll
-        for (int i = 0; i < NWD; i++) W[i] = words[i * blk_stride];
-        const uint64_t h = murmur_words<K>(W, seed);
-        if (!DIRTY || valid) emit(h);
-    }
-#endif
 }
 
 }  // namespace panib
