@@ -53,9 +53,9 @@ WORKLOADS = {
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures
 # profiles/r01_k1_ncu.md, r01_k2_ncu.md (config 2) and r01_k2c3_ncu.md (config 3); None = not captured.
 NCU_TRAFFIC_BYTES = {
-    ("config2", "k1"): 196.104192e6 + 7.778560e6,
-    ("config2", "k2"): 4.059136e6,
-    ("config3", "k2"): 40.328448e6 + 0.481536e6,
+    ("config2", "k1"): 195.848960e6 + 11.269120e6,
+    ("config2", "k2", "probe"): 4.059904e6,
+    ("config3", "k2", "probe"): 40.391680e6 + 0.887552e6,
 }
 
 
@@ -472,11 +472,14 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     roof_k2 = {"kernel": ("intersect_kernel (K2, probing form)" if stepper.k2_method == "probe" else
                           "index_* kernels (K2, inverted-index form: sort + AND/POPC bit matrix + rare-pair adds)"), "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                "frac": k2_gbs / peak,
-               "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k2")) if world == 1 else None,
+               "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k2", stepper.k2_method)) if world == 1 else None,
                "algorithmic_bytes": k2_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
                "bytes_per_pair": k2_bytes * world / max(1, n_pairs),
-               "note": "algorithmic bytes 8(|A|+|B|)+4 per pair; staged queries and L2-resident columns make "
-                       "DRAM traffic far smaller"}
+               "note": ("algorithmic bytes 8(|A|+|B|)+4 per pair; staged queries and L2-resident columns make "
+                        "DRAM traffic far smaller" if stepper.k2_method == "probe" else
+                        "algorithmic bytes keep SURVEY 8d's per-pair definition 8(|A|+|B|)+4, which the "
+                        "inverted-index form does not need to touch (it reads every sketch once, sorts the "
+                        "entries and works on shared hashes only), hence frac >> 1; its own cost is in stage_ms")}
     cpu = cpu_measure(args.workload, 2, 1) if not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
