@@ -233,9 +233,12 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly ONE line (the JSON): whatever libraries print there while the job runs
+    # (NCCL's version banner, for one) is sent to stderr; the descriptor is restored for the result
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = engine.Engine(local_rank)
     dev = eng.device
@@ -519,6 +522,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "result_checksum": checksum,
         "library": engine.library_version(),
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -358,6 +358,18 @@ def test_step_pipeline_eager_and_graph(eng) -> None:
     np.testing.assert_array_equal(out["identity_host"].numpy(), ident_eager.numpy())
     ident, _ = engine_ani_host(out["ov"], out["table"], k)
     np.testing.assert_allclose(out["identity_host"].numpy(), ident, rtol=0, atol=ANI_ATOL, equal_nan=True)
+    # the inverted-index K2 inside the step, eager and captured (CUB sort + scan inside the graph)
+    idx = pipeline.SourmashStep(eng, plan, bufs, tab, k, k2_method="index")
+    check(idx.run())
+    assert eng.last_intersect_method == "index"
+    assert idx.capture()
+    for _ in range(2):
+        out = idx.replay()
+        idx.finish()
+    check(out)
+    auto = pipeline.SourmashStep(eng, plan, bufs, tab, k)  # "auto" is resolved on the first step
+    check(auto.run())
+    assert auto.k2_method in ("probe", "index")
     # a size hint that is too small is reported, not silently truncated
     small = pipeline.SourmashStep(eng, plan, bufs, tab, k, size_hint=100)
     with pytest.raises(Exception, match="size_hint"):
