@@ -92,6 +92,14 @@ def summarise_launches(path: Path) -> str:
              "|---|---|---|---|---|"]
     for name, t in sorted(tot.items(), key=lambda kv: -kv[1]):
         lines.append(f"| `{name}` | {cnt[name]} | {t:.1f} | {100 * t / total:.1f}% | {t / cnt[name]:.1f} |")
+    step = {k: v for k, v in tot.items() if "panib::" in k and "synth" not in k and "pack_ascii" not in k}
+    if step:
+        st = sum(step.values())
+        top = max(step, key=step.get)
+        lines += ["", f"Kernels of the device-resident step only (panib kernels without the input generator and the "
+                  f"e2e pack): `{top}` = {100 * step[top] / st:.1f} % of their {st / 1e3:.2f} ms; the rest of the list "
+                  "is input generation, the L2 flush fills between steps and the e2e (host-input) passes, whose K1 "
+                  "runs as 16-32 chunk launches overlapped with the H2D copies."]
     return "\n".join(lines) + "\n"
 
 
