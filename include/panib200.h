@@ -169,19 +169,22 @@ PANIB_API int64_t panib_intersect_fence_entries(int64_t nq, int64_t ns, uint64_t
 /* ---- stage 2, inverted-index form (csrc/index.cu): same counts as panib_intersect(symmetric=1), cost
  * proportional to what the genomes SHARE instead of N^2 x sketch size.  Replaces the same reference step
  * (pyani_plus/methods/sourmash.py:184-200).  All sketches are flattened to (hash, genome) entries
- * (cap entries per genome, cap >= the largest sketch), sorted by hash; hashes held by >= tau genomes become
+ * sorted by hash; hashes held by >= tau genomes become
  * columns of a bit matrix (AND+POPC over all genome pairs), rarer shared hashes are expanded pair by pair.
- * d_work: scratch of panib_index_workspace_bytes(n, cap, tau) bytes, d_stats: uint64[4] written by
- * panib_index_build = {bit-matrix columns, pairs expanded from rare hashes, distinct hashes (+1), 0} so that
- * the caller can compare the cost with the probing kernel before calling panib_index_count with the SAME
- * n / max_hash / cap / tau / d_work.  Requires n * cap < 2^31 and max_hash < 2^64 - 16 (scaled >= 2).
- * A sketch larger than cap raises PANIB_ST_SEGMENT_OVERFLOW in d_status (re-plan with a larger cap).
+ * Entries: exact (d_offsets = int64[n+1] prefix sums of the sketch sizes, entries = their total) or padded
+ * (d_offsets NULL, entries = n * cap, unused slots hold a key above max_hash: needs no host knowledge of the
+ * sizes, so it can be captured in a CUDA graph); cap >= the largest sketch in both forms.
+ * d_work: scratch of panib_index_workspace_bytes(n, entries, tau) bytes, d_stats: uint64[4] written by
+ * panib_index_build = {bit-matrix columns, pairs expanded from rare hashes, distinct hashes (+1 if padded), 0}
+ * so that the caller can compare the cost with the probing kernel before calling panib_index_count with the
+ * SAME n / max_hash / entries / tau / d_work.  Requires entries < 2^31 and max_hash < 2^64 - 16 (scaled >= 2).
+ * A sketch larger than cap (or than its offsets slot) raises PANIB_ST_SEGMENT_OVERFLOW in d_status.
  * Multi-GPU: as panib_intersect (rank r computes the tiles / hashes it owns; the matrices sum). */
-PANIB_API int panib_index_workspace_bytes(int64_t n, int64_t cap, int tau, int64_t *bytes);
+PANIB_API int panib_index_workspace_bytes(int64_t n, int64_t entries, int tau, int64_t *bytes);
 PANIB_API int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts, int64_t stride, int64_t n,
-                      uint64_t max_hash, int64_t cap, int tau, void *d_work, int64_t work_bytes,
-                      uint64_t *d_stats, int32_t *d_status, void *stream);
-PANIB_API int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t cap, int tau,
+                      uint64_t max_hash, int64_t cap, int64_t entries, const int64_t *d_offsets, int tau,
+                      void *d_work, int64_t work_bytes, uint64_t *d_stats, int32_t *d_status, void *stream);
+PANIB_API int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t entries, int tau,
                       void *d_work, int64_t work_bytes, const uint64_t *d_stats, uint32_t *d_ov,
                       int64_t ld_ov, int rank, int world, int32_t *d_status, void *stream);
 

@@ -12,6 +12,10 @@
 //     (at most tau - 1 adds per entry);
 //   * hashes held by one genome contribute nothing and are dropped.
 //
+// The entries are either exact (offsets = prefix sums of the sketch sizes, computed by the caller) or
+// padded to `cap` slots per genome with a key above max_hash (no host knowledge of the sizes needed:
+// the form a captured CUDA graph uses).
+//
 // Results are identical to the probing kernel (exact integer counts); which form is cheaper depends
 // on the data, so the host chooses (engine.py: Engine.intersect(method="auto")) from the statistics
 // panib_index_build returns.  Replaces the same reference step as pairwise.cu: the external
@@ -39,6 +43,24 @@ index_flatten_kernel(const uint64_t *__restrict__ rows, const int32_t *__restric
     if (i == 0 && c > cap && status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);  // cap too small: re-plan
     keys[e] = i < c ? rows[(size_t)g * stride + i] : pad_key;
     vals[e] = (uint32_t)g;
+}
+
+// exact-size form: genome g's hashes go to entries offsets[g] .. offsets[g] + counts[g] (no pad entries);
+// grid = (chunks of the largest sketch, genomes)
+__global__ void __launch_bounds__(kIdxThreads)
+index_flatten_exact_kernel(const uint64_t *__restrict__ rows, const int32_t *__restrict__ counts, int64_t stride,
+                           int n, int cap, const int64_t *__restrict__ offsets, int64_t total,
+                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int32_t *status) {
+    const int i = blockIdx.x * kIdxThreads + threadIdx.x;
+    for (int g = blockIdx.y; g < n; g += gridDim.y) {
+        const int c = counts[g];
+        const int64_t at = offsets[g];
+        if (i == 0 && (c > cap || at + c > total) && status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);
+        if (i < c && i < cap && at + i < total) {
+            keys[at + i] = rows[(size_t)g * stride + i];
+            vals[at + i] = (uint32_t)g;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kIdxThreads)
@@ -197,13 +219,13 @@ struct IndexLayout {
     size_t off_keys[2], off_vals[2], off_bits, off_temp, temp_bytes, bytes;
 };
 
-static int index_layout(int64_t n, int64_t cap, int tau, IndexLayout *L) {
-    if (n <= 0 || cap <= 0 || tau < 2 || n * cap >= 0x7FFFFF00LL) {
-        set_error("panib_index: n=%lld cap=%lld tau=%d out of range (n*cap must be < 2^31)", (long long)n,
-                  (long long)cap, tau);
+static int index_layout(int64_t n, int64_t total, int tau, IndexLayout *L) {
+    if (n <= 0 || total <= 0 || tau < 2 || total >= 0x7FFFFF00LL) {
+        set_error("panib_index: n=%lld entries=%lld tau=%d out of range (entries must be < 2^31)", (long long)n,
+                  (long long)total, tau);
         return PANIB_E_ARG;
     }
-    L->total = n * cap;
+    L->total = total;
     L->wcap = (L->total / tau + 31) / 32 + 1;
     size_t sort_bytes = 0, scan_bytes = 0;
     if (cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
@@ -229,9 +251,9 @@ static int index_layout(int64_t n, int64_t cap, int tau, IndexLayout *L) {
 
 using namespace panib;
 
-extern "C" int panib_index_workspace_bytes(int64_t n, int64_t cap, int tau, int64_t *bytes) {
+extern "C" int panib_index_workspace_bytes(int64_t n, int64_t total, int tau, int64_t *bytes) {
     IndexLayout L;
-    int rc = index_layout(n, cap, tau, &L);
+    int rc = index_layout(n, total, tau, &L);
     if (rc) return rc;
     *bytes = (int64_t)L.bytes;
     return PANIB_OK;
@@ -240,11 +262,17 @@ extern "C" int panib_index_workspace_bytes(int64_t n, int64_t cap, int tau, int6
 // Phase 1: flatten, sort, find the runs, classify them.  d_stats (uint64[4]) receives
 // [0] frequent hashes (bit-matrix columns), [1] pairs the rare hashes expand to, [2] runs, [3] unused.
 extern "C" int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts, int64_t stride, int64_t n,
-                                 uint64_t max_hash, int64_t cap, int tau, void *d_work, int64_t work_bytes,
-                                 uint64_t *d_stats, int32_t *d_status, void *stream) {
+                                 uint64_t max_hash, int64_t cap, int64_t total, const int64_t *d_offsets, int tau,
+                                 void *d_work, int64_t work_bytes, uint64_t *d_stats, int32_t *d_status,
+                                 void *stream) {
     IndexLayout L;
-    int rc = index_layout(n, cap, tau, &L);
+    int rc = index_layout(n, total, tau, &L);
     if (rc) return rc;
+    if (cap <= 0 || cap > 0x7FFFFFFFLL || (!d_offsets && total != n * cap)) {
+        set_error("panib_index_build: cap=%lld / entries=%lld inconsistent (padded form needs entries == n*cap)",
+                  (long long)cap, (long long)total);
+        return PANIB_E_ARG;
+    }
     if (!d_work || work_bytes < (int64_t)L.bytes || !d_stats || max_hash >= 0xFFFFFFFFFFFFFFF0ull) {
         set_error("panib_index_build: workspace of %lld bytes given, %zu needed (or max_hash too large)",
                   (long long)work_bytes, L.bytes);
@@ -263,8 +291,14 @@ extern "C" int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts
     while (end_bit < 64 && (pad_key >> end_bit)) end_bit++;
 
     PANIB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(uint64_t), st));
-    index_flatten_kernel<<<blocks, kIdxThreads, 0, st>>>(d_rows, d_counts, stride, (int)n, (int)cap, pad_key,
-                                                         keys[0], vals[0], d_status);
+    if (d_offsets) {
+        const dim3 grid((unsigned)((cap + kIdxThreads - 1) / kIdxThreads), (unsigned)(n < 65535 ? n : 65535));
+        index_flatten_exact_kernel<<<grid, kIdxThreads, 0, st>>>(d_rows, d_counts, stride, (int)n, (int)cap, d_offsets,
+                                                                 T, keys[0], vals[0], d_status);
+    } else {
+        index_flatten_kernel<<<blocks, kIdxThreads, 0, st>>>(d_rows, d_counts, stride, (int)n, (int)cap, pad_key,
+                                                             keys[0], vals[0], d_status);
+    }
     rc = check_launch("index_flatten_kernel");
     if (rc) return rc;
     // keys[0]/vals[0] = flattened input, keys[1]/vals[1] = sorted output; after the sort the input
@@ -295,11 +329,11 @@ extern "C" int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts
 // Phase 2: intersection sizes from the index built by panib_index_build with the SAME arguments.
 // d_ov (uint32 [n x ld_ov]) is fully overwritten: counts for i != j (mirrored), sketch sizes on the
 // diagonal (rank 0 only, as panib_intersect); the ranks' matrices sum to the full result.
-extern "C" int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t cap, int tau,
+extern "C" int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t total, int tau,
                                  void *d_work, int64_t work_bytes, const uint64_t *d_stats, uint32_t *d_ov,
                                  int64_t ld_ov, int rank, int world, int32_t *d_status, void *stream) {
     IndexLayout L;
-    int rc = index_layout(n, cap, tau, &L);
+    int rc = index_layout(n, total, tau, &L);
     if (rc) return rc;
     if (!d_work || work_bytes < (int64_t)L.bytes || ld_ov < n || world < 1 || rank < 0 || rank >= world) {
         set_error("panib_index_count: bad workspace / ld_ov / rank arguments");

@@ -90,7 +90,7 @@ def load_library() -> ctypes.CDLL:
     L.panib_index_workspace_bytes.restype = _i32
     L.panib_index_workspace_bytes.argtypes = [_i64, _i64, _i32, ctypes.POINTER(_i64)]
     L.panib_index_build.restype = _i32
-    L.panib_index_build.argtypes = [_vp, _vp, _i64, _i64, _u64, _i64, _i32, _vp, _i64, _vp, _vp, _vp]
+    L.panib_index_build.argtypes = [_vp, _vp, _i64, _i64, _u64, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp]
     L.panib_index_count.restype = _i32
     L.panib_index_count.argtypes = [_vp, _i64, _u64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]
     L.panib_ani_device.restype = _i32
@@ -473,9 +473,9 @@ class Engine:
                 msg = "intersect(check=False) needs max_count (no device read is allowed)"
                 raise ValueError(msg)
             max_count = int(torch.maximum(q.counts.max(), s.counts.max()).item())
-        indexable = symmetric and nq >= 2 and mh < (1 << 64) - 16 and nq * max(1, max_count) < (1 << 31) - 512
+        indexable = symmetric and nq >= 2 and mh < (1 << 64) - 16
         if method == "index" and not indexable:
-            msg = "intersect(method='index') needs an all-vs-all call with n * max_count < 2^31 and scaled >= 2"
+            msg = "intersect(method='index') needs an all-vs-all call and scaled >= 2"
             raise ValueError(msg)
         if method == "auto" and (not indexable or not check):
             method = "probe"
@@ -526,26 +526,37 @@ class Engine:
         while True:
             cap = max(1, int(max_count))
             tau_ = tau if tau >= 2 else max(8, n // 32)
+            if check:  # exact entries: prefix sums of the sizes (one small read for their total)
+                offsets = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+                offsets[1:] = torch.cumsum(q.counts, 0, dtype=torch.int64)
+                total = int(offsets[-1].item())
+                off_ptr = offsets.data_ptr()
+                if total == 0 or total >= (1 << 31) - 512:
+                    return None  # nothing to index / too many entries: the probing kernel handles both
+            else:  # no device read allowed (graph capture): cap slots per genome, padded
+                offsets, total, off_ptr = None, n * cap, None
+                if total >= (1 << 31) - 512:
+                    return None
             need = _i64(0)
-            _check(self.lib.panib_index_workspace_bytes(n, cap, tau_, ctypes.byref(need)))
+            _check(self.lib.panib_index_workspace_bytes(n, total, tau_, ctypes.byref(need)))
             work = getattr(self, "_index_work", None)
             if work is None or work.numel() < need.value:
                 self._index_work = work = None  # free the old one first
                 self._index_work = work = torch.empty(need.value, dtype=torch.uint8, device=self.device)
                 self._index_stats = torch.zeros(4, dtype=torch.int64, device=self.device)
             stats = self._index_stats
-            _check(self.lib.panib_index_build(q.rows.data_ptr(), q.counts.data_ptr(), q.stride, n, mh, cap, tau_,
-                                              work.data_ptr(), work.numel(), stats.data_ptr(),
+            _check(self.lib.panib_index_build(q.rows.data_ptr(), q.counts.data_ptr(), q.stride, n, mh, cap, total,
+                                              off_ptr, tau_, work.data_ptr(), work.numel(), stats.data_ptr(),
                                               self.status.data_ptr(), self._stream()))
             if auto:
                 n_dense, rare_pairs, _, _ = stats.tolist()
-                est_index = (n * cap * self.COST_INDEX_PER_ENTRY + pairs * -(-n_dense // 32) * self.COST_INDEX_PER_WORD
+                est_index = (total * self.COST_INDEX_PER_ENTRY + pairs * -(-n_dense // 32) * self.COST_INDEX_PER_WORD
                              + rare_pairs / world * self.COST_INDEX_PER_RARE_PAIR)
                 self.last_intersect_estimates = {"probe_s": est_probe, "index_s": est_index,
                                                  "frequent_hashes": n_dense, "rare_pairs": rare_pairs}
                 if est_index >= est_probe:
                     return None
-            _check(self.lib.panib_index_count(q.counts.data_ptr(), n, mh, cap, tau_, work.data_ptr(), work.numel(),
+            _check(self.lib.panib_index_count(q.counts.data_ptr(), n, mh, total, tau_, work.data_ptr(), work.numel(),
                                               stats.data_ptr(), ov.data_ptr(), q.n, rank, world,
                                               self.status.data_ptr(), self._stream()))
             self.last_intersect_method = "index"
