@@ -173,12 +173,13 @@ PANIB_API int64_t panib_intersect_fence_entries(int64_t nq, int64_t ns, uint64_t
  * columns of a bit matrix (AND+POPC over all genome pairs), rarer shared hashes are expanded pair by pair.
  * Entries: exact (d_offsets = int64[n+1] prefix sums of the sketch sizes, entries = their total) or padded
  * (d_offsets NULL, entries = n * cap, unused slots hold a key above max_hash: needs no host knowledge of the
- * sizes, so it can be captured in a CUDA graph); cap >= the largest sketch in both forms.
+ * sizes, so it can be captured in a CUDA graph; cap >= the largest sketch, a larger one raises
+ * PANIB_ST_SEGMENT_OVERFLOW).  In the exact form cap only sizes the launch grid.
  * d_work: scratch of panib_index_workspace_bytes(n, entries, tau) bytes, d_stats: uint64[4] written by
  * panib_index_build = {bit-matrix columns, pairs expanded from rare hashes, distinct hashes (+1 if padded), 0}
  * so that the caller can compare the cost with the probing kernel before calling panib_index_count with the
  * SAME n / max_hash / entries / tau / d_work.  Requires entries < 2^31 and max_hash < 2^64 - 16 (scaled >= 2).
- * A sketch larger than cap (or than its offsets slot) raises PANIB_ST_SEGMENT_OVERFLOW in d_status.
+ * Offsets that do not match the sizes raise PANIB_ST_SEGMENT_OVERFLOW in d_status.
  * Multi-GPU: as panib_intersect (rank r computes the tiles / hashes it owns; the matrices sum). */
 PANIB_API int panib_index_workspace_bytes(int64_t n, int64_t entries, int tau, int64_t *bytes);
 PANIB_API int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts, int64_t stride, int64_t n,

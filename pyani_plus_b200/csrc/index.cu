@@ -51,14 +51,18 @@ __global__ void __launch_bounds__(kIdxThreads)
 index_flatten_exact_kernel(const uint64_t *__restrict__ rows, const int32_t *__restrict__ counts, int64_t stride,
                            int n, int cap, const int64_t *__restrict__ offsets, int64_t total,
                            uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int32_t *status) {
-    const int i = blockIdx.x * kIdxThreads + threadIdx.x;
+    // `cap` only sizes the grid: a genome larger than the hint is still flattened completely (strided loop)
+    (void)cap;
     for (int g = blockIdx.y; g < n; g += gridDim.y) {
         const int c = counts[g];
         const int64_t at = offsets[g];
-        if (i == 0 && (c > cap || at + c > total) && status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);
-        if (i < c && i < cap && at + i < total) {
-            keys[at + i] = rows[(size_t)g * stride + i];
-            vals[at + i] = (uint32_t)g;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (at < 0 || at + c > total) && status)
+            atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);  // offsets do not match the sizes
+        for (int i = blockIdx.x * kIdxThreads + threadIdx.x; i < c; i += gridDim.x * kIdxThreads) {
+            if (at + i < total) {
+                keys[at + i] = rows[(size_t)g * stride + i];
+                vals[at + i] = (uint32_t)g;
+            }
         }
     }
 }
@@ -109,13 +113,13 @@ index_classify_kernel(const uint64_t *__restrict__ keys, const int32_t *__restri
 
 __global__ void __launch_bounds__(kIdxThreads)
 index_bits_kernel(const uint32_t *__restrict__ vals, const int32_t *__restrict__ gidx,
-                  const int32_t *__restrict__ densecol, int64_t total, uint32_t *__restrict__ bits, int64_t wcap,
-                  int32_t *status) {
+                  const int32_t *__restrict__ densecol, int64_t total, int n, uint32_t *__restrict__ bits,
+                  int64_t wcap, int32_t *status) {
     const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
     if (e >= total) return;
     const int col = densecol[gidx[e] - 1];
     if (col < 0) return;
-    if ((col >> 5) >= wcap) {  // cannot happen when wcap was sized by panib_index_workspace_bytes
+    if ((col >> 5) >= wcap || vals[e] >= (uint32_t)n) {  // cannot happen with a consistent index
         if (status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);
         return;
     }
@@ -127,7 +131,7 @@ index_bits_kernel(const uint32_t *__restrict__ vals, const int32_t *__restrict__
 __global__ void __launch_bounds__(kIdxThreads)
 index_sparse_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                     const int32_t *__restrict__ gidx, const int32_t *__restrict__ start,
-                    const int32_t *__restrict__ densecol, int64_t total, uint64_t max_hash,
+                    const int32_t *__restrict__ densecol, int64_t total, int n, uint64_t max_hash,
                     uint32_t *__restrict__ ov, int64_t ld, int rank, int world) {
     const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
     if (e >= total) return;
@@ -136,7 +140,11 @@ index_sparse_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     if (world > 1 && r % world != rank) return;
     const int end = start[r + 1];
     const uint32_t i = vals[e];
-    for (int64_t x = e + 1; x < end; x++) atomicAdd(ov + (size_t)i * ld + vals[x], 1u);
+    if (i >= (uint32_t)n) return;
+    for (int64_t x = e + 1; x < end && x < total; x++) {
+        const uint32_t j = vals[x];
+        if (j < (uint32_t)n) atomicAdd(ov + (size_t)i * ld + j, 1u);
+    }
 }
 
 // frequent hashes: ov[i][j] += popcount(bits[i] & bits[j]) over the used words, for i < j.
@@ -353,10 +361,10 @@ extern "C" int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t ma
 
     PANIB_CUDA(cudaMemsetAsync(d_ov, 0, (size_t)n * ld_ov * sizeof(uint32_t), st));
     PANIB_CUDA(cudaMemsetAsync(bits, 0, (size_t)n * L.wcap * sizeof(uint32_t), st));
-    index_bits_kernel<<<blocks, kIdxThreads, 0, st>>>(svals, gidx, densecol, T, bits, L.wcap, d_status);
+    index_bits_kernel<<<blocks, kIdxThreads, 0, st>>>(svals, gidx, densecol, T, (int)n, bits, L.wcap, d_status);
     rc = check_launch("index_bits_kernel");
     if (rc) return rc;
-    index_sparse_kernel<<<blocks, kIdxThreads, 0, st>>>(skeys, svals, gidx, start, densecol, T, max_hash, d_ov,
+    index_sparse_kernel<<<blocks, kIdxThreads, 0, st>>>(skeys, svals, gidx, start, densecol, T, (int)n, max_hash, d_ov,
                                                         ld_ov, rank, world);
     rc = check_launch("index_sparse_kernel");
     if (rc) return rc;
