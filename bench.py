@@ -143,6 +143,25 @@ class ClockSampler:
         }
 
 
+K1_WARP_INST_PER_KMER = 144.0  # ncu: smsp__inst_executed.sum / (k-mers / 32), profiles/r01_k1_ncu.md
+
+
+def integer_pipe_view(bases: int, k1_ms: float, clocks: dict | None) -> dict:
+    """What actually bounds K1: issue slots / the two half-rate integer pipes, from the live kernel time.
+
+    Warp instructions per k-mer are a property of the compiled kernel (taken from the committed ncu
+    capture); time and SM clock are measured in this run.  A B200 SM issues at most one warp
+    instruction per cycle on each of its 4 schedulers; the ALU and FMA-heavy pipes take one per two
+    cycles each, and K1's instructions split about evenly between them, so ~1.0 is the ceiling.
+    """
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    warp_inst = bases / 32.0 * K1_WARP_INST_PER_KMER
+    slots = k1_ms * 1e-3 * mhz * 1e6 * 148 * 4
+    return {"warp_inst_per_kmer": K1_WARP_INST_PER_KMER, "source": "profiles/r01_k1_ncu.md",
+            "issue_slot_frac": warp_inst / slots, "sm_mhz_used": mhz,
+            "ncu_pipe_busy": {"alu": 0.702, "fma_heavy": 0.706, "issue": 0.737, "dram": 0.009}}
+
+
 # ======================================================================================= CPU arm
 def cpu_measure(workload: str, steps: int, warmup: int, budget_s: float = 25.0) -> dict:
     """Time the oracle port (all host threads) on a bounded sample of the workload.
@@ -471,7 +490,8 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                "algorithmic_bytes": k1_bytes, "peak_source": peak_src,
                "ms_per_launch": k1_hash_ms, "bytes_per_bp": 0.25 + 0.125 + 8.0 / scaled,
                "note": "integer-ALU bound by construction (MurmurHash3 over 31 ASCII bytes per base); see "
-                       "DESIGN.md and profiles/ for pipe utilisation"}
+                       "DESIGN.md and profiles/ for pipe utilisation",
+               "integer_pipes": integer_pipe_view(local_bases, k1_hash_ms, dev_t["clocks"])}
     roof_k2 = {"kernel": ("intersect_kernel (K2, probing form)" if stepper.k2_method == "probe" else
                           "index_* kernels (K2, inverted-index form: sort + AND/POPC bit matrix + rare-pair adds)"), "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                "frac": k2_gbs / peak,
