@@ -106,3 +106,36 @@ def test_product_never_imports_oracle() -> None:
             text = path.read_text()
             assert "import oracle" not in text and "from oracle" not in text, path
             assert "liboracle" not in text, path
+
+
+def _prototypes() -> dict[str, list[str]]:
+    """name -> list of C parameter declarations, parsed from the header."""
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"PANIB_API\s+[\w\s\*]+?\b(panib_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params == ["void"] else params
+    return out
+
+
+def test_ctypes_binding_matches_header(lib: ctypes.CDLL) -> None:
+    """Every bound function has as many argtypes as the header has parameters, pointers are bound as
+    pointers and 64-bit integers as 64-bit (a drifted binding would pass truncated pointers)."""
+    protos = _prototypes()
+    assert len(protos) >= 20
+    checked = 0
+    for name, params in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            assert not params or name in ("panib_version", "panib_device_count", "panib_launch_count"), name
+            continue
+        assert len(fn.argtypes) == len(params), f"{name}: {len(fn.argtypes)} argtypes, {len(params)} parameters"
+        for ctype, decl in zip(fn.argtypes, params, strict=True):
+            is_ptr = "*" in decl
+            size = ctypes.sizeof(ctype)
+            if is_ptr or re.search(r"\b(u?int64_t|size_t|double)\b", decl):
+                assert size == 8, f"{name}: '{decl}' bound as {ctype}"
+            else:
+                assert size == 4, f"{name}: '{decl}' bound as {ctype}"
+        checked += 1
+    assert checked >= 15
