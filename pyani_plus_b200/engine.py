@@ -233,6 +233,9 @@ class Engine:
         self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.last_max_count = 0
         self.last_intersect_method = ""
+        self._index_work = None            # inverted-index K2: scratch of the checked (eager) calls
+        self._index_work_fixed: dict = {}  # ... and of enqueue-only calls, by (n, entries, tau): graph-safe
+        self._index_stats = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.last_intersect_estimates: dict = {}
         self.max_batch_bytes = 1 << 31  # ASCII bytes staged per sketch batch
 
@@ -539,11 +542,17 @@ class Engine:
                     return None
             need = _i64(0)
             _check(self.lib.panib_index_workspace_bytes(n, total, tau_, ctypes.byref(need)))
-            work = getattr(self, "_index_work", None)
-            if work is None or work.numel() < need.value:
-                self._index_work = work = None  # free the old one first
-                self._index_work = work = torch.empty(need.value, dtype=torch.uint8, device=self.device)
-                self._index_stats = torch.zeros(4, dtype=torch.int64, device=self.device)
+            if check:  # eager calls share one workspace that grows on demand
+                work = self._index_work
+                if work is None or work.numel() < need.value:
+                    self._index_work = work = None  # free the old one first
+                    self._index_work = work = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            else:  # enqueue-only calls may sit in a captured graph: their workspace is never freed or resized
+                key = (n, total, tau_)
+                work = self._index_work_fixed.get(key)
+                if work is None:
+                    work = self._index_work_fixed[key] = torch.empty(need.value, dtype=torch.uint8,
+                                                                     device=self.device)
             stats = self._index_stats
             _check(self.lib.panib_index_build(q.rows.data_ptr(), q.counts.data_ptr(), q.stride, n, mh, cap, total,
                                               off_ptr, tau_, work.data_ptr(), work.numel(), stats.data_ptr(),
