@@ -221,6 +221,10 @@ def run_reference(args: argparse.Namespace) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun sets OMP_NUM_THREADS=1 for its workers; this arm runs on rank 0 alone and must use
+        # every host thread it can (set before the OpenMP runtime of the oracle library starts)
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     n, length, k, scaled, desc = WORKLOADS[args.workload]
     base = cpu_measure(args.workload, args.steps, args.warmup, budget_s=120.0)
     line = {
@@ -503,7 +507,8 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                         "algorithmic bytes keep SURVEY 8d's per-pair definition 8(|A|+|B|)+4, which the "
                         "inverted-index form does not need to touch (it reads every sketch once, sorts the "
                         "entries and works on shared hashes only), hence frac >> 1; its own cost is in stage_ms")}
-    cpu = cpu_measure(args.workload, 2, 1) if not args.no_cpu_baseline else None
+    # the CPU leg runs at N=1 only (under torchrun the workers are pinned to one OpenMP thread)
+    cpu = cpu_measure(args.workload, 2, 1) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_t["ms"], "higher_is_better": True, "scaling": "strong",
