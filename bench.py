@@ -50,13 +50,59 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures
-# profiles/r01_k1_ncu.md, r01_k2_ncu.md (config 2) and r01_k2c3_ncu.md (config 3); None = not captured.
-NCU_TRAFFIC_BYTES = {
-    ("config2", "k1"): 195.848960e6 + 11.269120e6,
-    ("config2", "k2", "probe"): 4.059904e6,
-    ("config3", "k2", "probe"): 40.391680e6 + 0.887552e6,
-}
+def kernel_source_sha() -> str:
+    """sha256 over the CUDA sources the library is built from: ties an ncu capture to the kernels it measured."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = ROOT / "pyani_plus_b200" / "csrc"
+    for f in sorted(list(csrc.glob("*.cu")) + list(csrc.glob("*.cuh")) + [ROOT / "include" / "panib200.h"]):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture(workload: str, kernel: str) -> dict | None:
+    """Per-launch ncu numbers of ``kernel`` ("k1", "k2_probe", "k2_index") at ``workload`` from the newest
+    profiles/ncu_r*.json (written by tools/ncu_to_json.py from an ``ncu --set full`` capture) -- but only if
+    that capture was taken from the kernel sources this tree holds; otherwise None (stale = not evidence)."""
+    files = sorted((ROOT / "profiles").glob("ncu_r*.json"))
+    if not files:
+        return None
+    try:
+        data = json.loads(files[-1].read_text())
+    except ValueError:
+        return None
+    if data.get("source_sha") != kernel_source_sha():
+        return None
+    cap = data.get("captures", {}).get(workload, {}).get(kernel)
+    if cap is not None:
+        cap = dict(cap, file=f"profiles/{files[-1].name}")
+    return cap
+
+
+def config_dict(workload: str, n_gpus: int) -> dict:
+    """The ``config`` object of the JSON line: a function of (workload, N) only, so that the GPU arm and the
+    reference arm print the same one."""
+    n, length, k, scaled, desc = WORKLOADS[workload]
+    return {"workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled,
+            "pairs": n * (n - 1) // 2, "seed": SEED, "l2": "flushed between steps (256 MiB write)",
+            "parallelism": (f"genomes sliced over {n_gpus} ranks for K1, one exchange of the sketches over "
+                            "NVLink, K2 work sharded by rank") if n_gpus > 1 else "single GPU"}
+
+
+def expected_checksum(workload: str) -> dict | None:
+    """Oracle-pinned result checksum of a workload (tools/oracle_checksums.py), or None if not pinned."""
+    p = ROOT / "tests" / "golden" / "workload_checksums.json"
+    if not p.is_file():
+        return None
+    e = json.loads(p.read_text()).get(workload)
+    return {k_: e[k_] for k_ in ("ov_weighted_sum", "hash_sum", "sketch_total")} if e else None
+
+
+def checksum_weights(rows, cols):
+    """Position weights of the count-matrix checksum (numpy int64 arrays or torch int64 tensors)."""
+    return (rows[:, None] * 1000003 + cols[None, :] * 7919 + 1) % 2147483647
 
 
 def hbm_peak() -> tuple[float, str]:
@@ -143,48 +189,65 @@ class ClockSampler:
         }
 
 
-K1_WARP_INST_PER_KMER = 144.0  # ncu: smsp__inst_executed.sum / (k-mers / 32), profiles/r01_k1_ncu.md
+def integer_pipe_view(bases: int, k1_ms: float, clocks: dict | None, cap: dict | None) -> dict:
+    """What actually bounds K1: issue slots and the two half-rate integer pipes.
 
-
-def integer_pipe_view(bases: int, k1_ms: float, clocks: dict | None) -> dict:
-    """What actually bounds K1: issue slots / the two half-rate integer pipes, from the live kernel time.
-
-    Warp instructions per k-mer are a property of the compiled kernel (taken from the committed ncu
-    capture); time and SM clock are measured in this run.  A B200 SM issues at most one warp
-    instruction per cycle on each of its 4 schedulers; the ALU and FMA-heavy pipes take one per two
-    cycles each, and K1's instructions split about evenly between them, so ~1.0 is the ceiling.
+    Warp instructions per launch and the pipe-busy percentages come from the ncu capture of THESE kernel
+    sources (``ncu_capture``; null when the committed capture is of other sources); time and SM clock are
+    measured in this run.  A B200 SM issues at most one warp instruction per cycle on each of its 4
+    schedulers; the ALU and FMA-heavy pipes take one per two cycles each.
     """
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    warp_inst = bases / 32.0 * K1_WARP_INST_PER_KMER
     slots = k1_ms * 1e-3 * mhz * 1e6 * 148 * 4
-    return {"warp_inst_per_kmer": K1_WARP_INST_PER_KMER, "source": "profiles/r01_k1_ncu.md",
-            "issue_slot_frac": warp_inst / slots, "sm_mhz_used": mhz,
-            "ncu_pipe_busy": {"alu": 0.702, "fma_heavy": 0.706, "issue": 0.737, "dram": 0.009}}
+    out = {"sm_mhz_used": mhz, "issue_slots_in_launch": slots, "warp_inst_per_kmer": None, "issue_slot_frac": None,
+           "ncu_pipe_busy": None, "source": None}
+    if cap and cap.get("inst_executed") and cap.get("bases"):
+        per_kmer = cap["inst_executed"] / (cap["bases"] / 32.0)
+        out.update({"warp_inst_per_kmer": per_kmer, "issue_slot_frac": bases / 32.0 * per_kmer / slots,
+                    "ncu_pipe_busy": cap.get("pipe_busy"), "source": cap.get("file")})
+    return out
 
 
 # ======================================================================================= CPU arm
 def cpu_measure(workload: str, steps: int, warmup: int, budget_s: float = 25.0) -> dict:
-    """Time the oracle port (all host threads) on a bounded sample of the workload.
+    """Time the oracle port (all host threads) on the workload, or on a bounded sample of it.
 
-    Returns whole-job pairs/s extrapolated to the full workload: sketching scales linearly in the
-    number of genomes, intersection linearly in the number of pairs.
+    The whole workload is timed when ``steps + warmup`` passes of it fit ``budget_s`` (estimated from a
+    one-genome probe); otherwise the largest genome subset that fits, and the whole-job time is
+    extrapolated: sketching scales linearly in the number of genomes, intersection in the number of pairs.
     """
     from oracle import oracle
 
     n, length, k, scaled, _ = WORKLOADS[workload]
     threads = oracle.num_threads()
     n_pairs = n * (n - 1) // 2
-    # sample: enough genomes to keep every thread busy, bounded so a step stays within seconds
-    per_genome_s = length / 45e6  # ~45 Mbp/s/core for the scalar port
-    ns = int(max(4, min(n, threads * max(1, int(budget_s / max(1, steps + warmup) / per_genome_s)))))
-    ns = min(ns, 200)
-    seqs = np.empty((ns, length), dtype=np.uint8)
-    for g in range(ns):
-        seqs[g] = np.frombuffer(oracle.synth_genome(SEED, g, length), dtype=np.uint8)
+    lib = oracle.lib()
     cap = int(length / scaled * 1.5) + 256
+    # probe: one genome per thread, to size the sample from this machine's speed
+    np_ = min(n, threads)
+    probe = np.empty((np_, length), dtype=np.uint8)
+    for g in range(np_):
+        probe[g] = np.frombuffer(oracle.synth_genome(SEED, g, length), dtype=np.uint8)
+    out = np.zeros((np_, cap), dtype=np.uint64)
+    counts = np.zeros(np_, dtype=np.int64)
+    t0 = time.perf_counter()
+    lib.oracle_sketch_batch(probe.ctypes.data, np_, length, k, oracle.max_hash(scaled),
+                            out.ctypes.data_as(oracle.c_u64p), cap, counts.ctypes.data_as(oracle.c_i64p))
+    per_genome_s = (time.perf_counter() - t0) / np_  # wall seconds per genome with all threads busy
+    per_step = budget_s / max(1, steps + warmup)
+    pair_s = 2.5e-6 * (1000.0 / scaled) * 16 / max(1, threads)  # rough merge cost per pair, only sizes the sample
+    ns = n
+    if n * per_genome_s + n_pairs * pair_s > per_step:
+        ns = int(max(min(n, threads), min(n, per_step / (per_genome_s + pair_s * n / 2))))
+        while ns > threads and ns * per_genome_s + ns * (ns - 1) / 2 * pair_s > per_step:
+            ns = int(ns * 0.9)
+    seqs = np.empty((ns, length), dtype=np.uint8)
+    seqs[:np_] = probe[:min(np_, ns)] if ns >= np_ else probe[:ns]
+    for g in range(min(np_, ns), ns):
+        seqs[g] = np.frombuffer(oracle.synth_genome(SEED, g, length), dtype=np.uint8)
+    del probe
     out = np.zeros((ns, cap), dtype=np.uint64)
     counts = np.zeros(ns, dtype=np.int64)
-    lib = oracle.lib()
     t_sk, t_ix = [], []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -192,28 +255,27 @@ def cpu_measure(workload: str, steps: int, warmup: int, budget_s: float = 25.0) 
                                 out.ctypes.data_as(oracle.c_u64p), cap, counts.ctypes.data_as(oracle.c_i64p))
         t1 = time.perf_counter()
         ov = oracle.intersect_all(out, counts)
-        t2 = time.perf_counter()
-        # ANI finalisation is part of the path
+        # ANI finalisation is part of the path (one row's worth: the Python loop is not what is measured)
         for i in range(min(ns, 64)):
             oracle.pair_row(int(ov[0, i]), int(counts[0]), int(counts[i]), k)
+        t2 = time.perf_counter()
         if it >= warmup:
             t_sk.append(t1 - t0)
             t_ix.append(t2 - t1)
     sk = float(np.mean(t_sk))
     ix = float(np.mean(t_ix))
     s_pairs = ns * (ns - 1) // 2
-    full_s = sk * (n / ns) + ix * (n_pairs / max(1, s_pairs))
+    full = ns == n
+    full_s = sk + ix if full else sk * (n / ns) + ix * (n_pairs / max(1, s_pairs))
+    sample = (f"the whole workload per step: {n} genomes sketched ({sk:.3f} s) and all {n_pairs} pairs "
+              f"intersected ({ix:.4f} s)" if full else
+              f"{ns} of {n} genomes sketched ({sk:.3f} s) and their {s_pairs} pairs intersected ({ix:.4f} s) "
+              f"per step, extrapolated linearly in genomes / pairs to the full workload")
     return {
-        "value": n_pairs / full_s,
-        "unit": UNIT,
-        "cores": threads,
-        "kind": "port",
-        "sample": (f"{ns} of {n} genomes sketched ({sk:.3f} s) and their {s_pairs} pairs intersected "
-                   f"({ix:.4f} s) per step, extrapolated linearly in genomes / pairs to the full workload"),
+        "value": n_pairs / full_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
         "sketch_gbp_s": ns * length / sk / 1e9,
         "pairs_per_s_intersect": s_pairs / ix if ix > 0 else None,
-        "step_s": sk + ix,
-        "full_workload_s": full_s,
+        "step_s": sk + ix, "full_workload_s": full_s, "sampled_genomes": ns, "extrapolated": not full,
     }
 
 
@@ -225,19 +287,19 @@ def run_reference(args: argparse.Namespace) -> None:
         # torchrun sets OMP_NUM_THREADS=1 for its workers; this arm runs on rank 0 alone and must use
         # every host thread it can (set before the OpenMP runtime of the oracle library starts)
         os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
-    n, length, k, scaled, desc = WORKLOADS[args.workload]
-    base = cpu_measure(args.workload, args.steps, args.warmup, budget_s=120.0)
+    base = cpu_measure(args.workload, args.steps, args.warmup, budget_s=args.reference_budget)
     line = {
         "impl": "reference",
         "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": base["full_workload_s"] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled,
-                   "note": "pyani-plus's real CPU path (sourmash + branchwater, Rust) is not installable "
-                           "here; this arm times the oracle CPU port of the same algorithm with OpenMP"},
+        "config": config_dict(args.workload, args.gpus),
+        "note": "pyani-plus's real CPU path (sourmash + branchwater, Rust) is not installable here; this arm "
+                "times the oracle CPU port of the same algorithm with OpenMP on all host threads",
         "cpu_baseline": {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
         "sketch_gbp_s": base["sketch_gbp_s"],
         "pairs_per_s_intersect": base["pairs_per_s_intersect"],
+        "measured_step_s": base["step_s"], "extrapolated": base["extrapolated"],
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -454,7 +516,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     ov_ck = torch.zeros(1, dtype=torch.int64, device=dev)
     for r0 in range(0, n, 1024):  # row blocks keep the int64 temporaries small at 10,000 genomes
         blk = result["ov"][real[r0: r0 + 1024]][:, real].to(torch.int64)
-        w = (idx[r0: r0 + 1024, None] * 1000003 + idx[None, :] * 7919 + 1) % 2147483647
+        w = checksum_weights(idx[r0: r0 + 1024], idx)
         ov_ck += (blk * w).sum()
     if world > 1:
         dist.all_reduce(ov_ck, op=dist.ReduceOp.SUM)  # the ranks hold disjoint parts of the matrix
@@ -463,6 +525,11 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     hash_ck = int((rows_real * valid).sum().item())  # wrapping int64 sum of every sketch hash
     checksum = {"ov_weighted_sum": int(ov_ck.item()), "hash_sum": hash_ck, "sketch_total": int(counts_host.sum())}
     del rows_real, valid
+    # parity gate: the oracle's checksum of the COMPLETE workload (tests/golden/workload_checksums.json)
+    expected = expected_checksum(args.workload)
+    parity = {"expected": expected, "ok": (checksum == expected) if expected else None,
+              "source": "tests/golden/workload_checksums.json (tools/oracle_checksums.py)" if expected else
+                        "workload not pinned"}
 
     e2e_t = None
     if do_e2e:
@@ -488,18 +555,20 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     value = n_pairs / (dev_t["ms"] * 1e-3)
     e2e_value = n_pairs / (e2e_t["ms"] * 1e-3) if e2e_t else None
     dominant_is_k1 = dev_t["k1_ms"] >= dev_t["k2_ms"]
+    cap_k1 = ncu_capture(args.workload, "k1")
+    cap_k2 = ncu_capture(args.workload, "k2_" + stepper.k2_method)
     roof_k1 = {"kernel": "sketch_hash_kernel<31> (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peak,
                "unit": "GB/s", "frac": k1_gbs / peak,
-               "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k1")) if world == 1 else None,
+               "traffic": (cap_k1 or {}).get("dram_bytes") if world == 1 else None,
                "algorithmic_bytes": k1_bytes, "peak_source": peak_src,
                "ms_per_launch": k1_hash_ms, "bytes_per_bp": 0.25 + 0.125 + 8.0 / scaled,
                "note": "integer-ALU bound by construction (MurmurHash3 over 31 ASCII bytes per base); see "
                        "DESIGN.md and profiles/ for pipe utilisation",
-               "integer_pipes": integer_pipe_view(local_bases, k1_hash_ms, dev_t["clocks"])}
+               "integer_pipes": integer_pipe_view(local_bases, k1_hash_ms, dev_t["clocks"], cap_k1)}
     roof_k2 = {"kernel": ("intersect_kernel (K2, probing form)" if stepper.k2_method == "probe" else
                           "index_* kernels (K2, inverted-index form: sort + AND/POPC bit matrix + rare-pair adds)"), "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                "frac": k2_gbs / peak,
-               "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "k2", stepper.k2_method)) if world == 1 else None,
+               "traffic": (cap_k2 or {}).get("dram_bytes") if world == 1 else None,
                "algorithmic_bytes": k2_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
                "bytes_per_pair": k2_bytes * world / max(1, n_pairs),
                "note": ("algorithmic bytes 8(|A|+|B|)+4 per pair; staged queries and L2-resident columns make "
@@ -513,12 +582,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_t["ms"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled,
-                   "pairs": n_pairs, "seed": SEED, "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": (f"genomes sliced over {world} ranks for K1, "
-                                   + ("finalize fused with the all-gather (peer-memory stores over NVLink)"
-                                      if fused is not None else "NCCL all-gather of sketch rows")
-                                   + ", K2 work items round-robin") if world > 1 else "single GPU"},
+        "config": config_dict(args.workload, world),
+        "exchange": (("finalize fused with the all-gather (peer-memory stores over NVLink)" if fused is not None
+                      else "NCCL all-gather of sketch rows") if world > 1 else None),
         "sketch_gbp_s": n * length / (dev_t["k1_ms"] * 1e-3) / 1e9,
         "pairs_per_s_k2": n_pairs / (dev_t["k2_ms"] * 1e-3),
         "stage_ms": {"k1_sketch": dev_t["k1_ms"], "allgather": dev_t["gather_ms"], "k2_intersect": dev_t["k2_ms"],
@@ -545,6 +611,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "clocks": dev_t["clocks"],
         "sketch_sizes": {"mean": float(counts_host.mean()), "max": int(counts_host.max())},
         "result_checksum": checksum,
+        "parity": parity,
         "library": engine.library_version(),
     }
     sys.stdout.flush()
@@ -553,6 +620,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity["ok"] is False:
+        print(f"PARITY FAILURE: result checksum {checksum} != oracle {expected}", file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 def main() -> None:
@@ -561,7 +631,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config3")
+    ap.add_argument("--reference-budget", type=float, default=240.0,
+                    help="--impl reference: seconds of CPU work the whole run may take; the full workload is "
+                         "timed every step when it fits, else a bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--k2", default="auto", choices=["auto", "probe", "index"],

@@ -32,7 +32,8 @@ struct Collect {
     uint64_t *out;
     int64_t cap;
     int64_t n;
-    void operator()(uint64_t h) {
+    void operator()(const Partial &p) {
+        const uint64_t h = p.hash();
         if (h != 0ull && h <= max_hash) {
             if (n < cap) out[n] = h;
             n++;
@@ -44,17 +45,27 @@ template <int K>
 static int64_t run(const uint32_t *packed, const uint32_t *mask, int64_t t0, int64_t t1, uint32_t seed,
                    uint64_t max_hash, uint64_t *out, int64_t cap) {
     Collect c{max_hash, out, cap, 0};
+    const HashConsts hc = make_hash_consts(seed, max_hash);
     constexpr int S = kTileBases / kCtaTile;  // CTA tiles per stream tile
+    static uint32_t stage[kSpLead + kTileWords];          // the kernel's staged tile with its lead-in words
+    static uint32_t rcp_[kSpLead + kTileWords];           // packed reverse stream (phase A -> phase B)
+    static uint32_t scratch[2 * kBlkWords * kThreadsK1];  // all threads' scratch blocks (shared memory on the GPU)
     for (int64_t tile = t0 * S; tile < t1 * S; tile++) {
-        const uint32_t *sp = packed + tile * (kCtaTile / 16);
         const uint32_t *sm = mask + tile * (kCtaTile / 32);
+        for (int i = 0; i < kSpLead; i++) stage[i] = 0xDEADBEEFu;  // content must not matter
+        memcpy(stage + kSpLead, packed + tile * (kCtaTile / 16), sizeof(uint32_t) * kTileWords);
+        const uint32_t *sp = stage + kSpLead;
+        uint32_t *rcp = rcp_ + kSpLead;
+        for (int i = 0; i < kSpLead; i++) rcp_[i] = 0x13572468u;
         uint32_t any = 0;
         for (int i = 0; i < kTileMaskWords; i++) any |= sm[i];
+        for (size_t i = 0; i < sizeof(scratch) / sizeof(scratch[0]); i++) scratch[i] = 0xA5A5A5A5u;
+        for (int t = 0; t < Geom<K>::NI; t++) tile_expand_item<K>(sp, rcp, scratch, kThreadsK1, t);
+        for (int lane = 0; lane < 32; lane++) tile_expand_halo<K>(sp, rcp, scratch, kThreadsK1, lane);
         for (int tid = 0; tid < kThreadsK1; tid++) {
             const int u = tid >> 2, a = tid & 3;
-            uint32_t blk[2 * kBlkWords];  // the thread's scratch block (shared memory on the GPU)
-            if (any) hash_thread_kmers<K, true>(sp, sm, blk, 1, u, a, seed, c);
-            else hash_thread_kmers<K, false>(sp, sm, blk, 1, u, a, seed, c);
+            const uint32_t vmask = any ? thread_valid_mask<K>(sm, u, a) : 0xFFFFu;
+            hash_thread_kmers<K>(sp, rcp, scratch + tid, kThreadsK1, u, a, vmask, hc, c);
         }
     }
     return c.n;

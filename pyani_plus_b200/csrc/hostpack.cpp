@@ -1,0 +1,286 @@
+// hostpack.cpp -- host side of the ingest pipeline of libpanib200.so: ASCII base stream -> 2-bit packed words +
+// validity mask on a persistent pool of host threads (AVX-512 / AVX2 / scalar, chosen at run time).
+//
+// Why on the host: the sketch path is fed over PCIe.  An ASCII base is 1 byte, its packed form 0.375 byte
+// (2 bits + 1 validity bit), so packing BEFORE the copy cuts the bytes on the link by 2.7x (SURVEY.md 8f-1:
+// "pack+mask emitted by the reader, pinned buffers, overlap with K1").  The reference reads FASTA through
+// pyani_plus/utils.py:40-90 (fasta_bytes_iterator) and hands whole files to `sourmash scripts singlesketch`
+// (pyani_plus/methods/sourmash.py:67-83); this is the ingest stage of the replacement.
+//
+// The packed format is the device format of pack.cuh / panib_pack_ascii: 16 bases per uint32, base i at
+// bits 2i, A=0 C=1 G=2 T=3 (case-insensitive), invalid bases packed as 0 with their bit set in the mask
+// (1 bit per base, 32 bases per uint32).  tests/test_abi.py checks the three code paths against each other;
+// the GPU tests check the host form against panib_pack_ascii.
+#include <immintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <sched.h>
+
+#include "../../include/panib200.h"
+
+namespace panib {
+void set_error(const char *fmt, ...);
+
+// ---- one block of 32*m bases ----------------------------------------------------------------------------
+static void pack_block_scalar(const uint8_t *a, int64_t n_groups, uint32_t *packed, uint32_t *mask) {
+    static uint8_t lut[256];
+    static std::atomic<bool> ready{false};
+    if (!ready.load(std::memory_order_acquire)) {
+        uint8_t t[256];
+        memset(t, 0x80, sizeof t);  // bit 7 = invalid
+        t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+        memcpy(lut, t, sizeof t);
+        ready.store(true, std::memory_order_release);
+    }
+    for (int64_t g = 0; g < n_groups; g++) {
+        uint64_t p = 0;
+        uint32_t inv = 0;
+        for (int i = 0; i < 32; i++) {
+            const uint8_t c = lut[a[32 * g + i]];
+            p |= (uint64_t)(c & 3u) << (2 * i);
+            inv |= (uint32_t)(c >> 7) << i;
+        }
+        packed[2 * g] = (uint32_t)p;
+        packed[2 * g + 1] = (uint32_t)(p >> 32);
+        mask[g] = inv;
+    }
+}
+
+__attribute__((target("avx2"))) static void pack_block_avx2(const uint8_t *a, int64_t n_groups, uint32_t *packed,
+                                                           uint32_t *mask) {
+    const __m256i up = _mm256_set1_epi8((char)0xDF);
+    const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'),
+                  cT = _mm256_set1_epi8('T');
+    const __m256i m3 = _mm256_set1_epi8(3), m1 = _mm256_set1_epi8(1);
+    const __m256i w14 = _mm256_set1_epi16(0x0401);      // bytes (1, 4): c0 + 4 c1
+    const __m256i w116 = _mm256_set1_epi32(0x00100001);  // words (1, 16): + 16 (c2 + 4 c3)
+    const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    for (int64_t g = 0; g < n_groups; g++) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(a + 32 * g));
+        const __m256i u = _mm256_and_si256(v, up);
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+        // code = ((u >> 1) & 3) ^ ((u >> 2) & 1), zero where invalid
+        __m256i code = _mm256_xor_si256(_mm256_and_si256(_mm256_srli_epi16(u, 1), m3),
+                                        _mm256_and_si256(_mm256_srli_epi16(u, 2), m1));
+        code = _mm256_and_si256(code, ok);
+        const __m256i b = _mm256_madd_epi16(_mm256_maddubs_epi16(code, w14), w116);  // one byte per 4 bases
+        const __m256i q = _mm256_shuffle_epi8(b, pick);                              // 4 bytes per 128-bit lane
+        packed[2 * g] = (uint32_t)_mm256_extract_epi32(q, 0);
+        packed[2 * g + 1] = (uint32_t)_mm256_extract_epi32(q, 4);
+        mask[g] = ~(uint32_t)_mm256_movemask_epi8(ok);
+    }
+}
+
+__attribute__((target("avx512f,avx512bw"))) static void pack_block_avx512(const uint8_t *a, int64_t n_groups,
+                                                                          uint32_t *packed, uint32_t *mask) {
+    const __m512i up = _mm512_set1_epi8((char)0xDF);
+    const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'),
+                  cT = _mm512_set1_epi8('T');
+    const __m512i m3 = _mm512_set1_epi8(3), m1 = _mm512_set1_epi8(1);
+    const __m512i w14 = _mm512_set1_epi16(0x0401), w116 = _mm512_set1_epi32(0x00100001);
+    int64_t g = 0;
+    for (; g + 2 <= n_groups; g += 2) {  // 64 bases per iteration
+        const __m512i v = _mm512_loadu_si512(a + 32 * g);
+        const __m512i u = _mm512_and_si512(v, up);
+        const __mmask64 ok = _mm512_cmpeq_epi8_mask(u, cA) | _mm512_cmpeq_epi8_mask(u, cC) |
+                             _mm512_cmpeq_epi8_mask(u, cG) | _mm512_cmpeq_epi8_mask(u, cT);
+        __m512i code = _mm512_xor_si512(_mm512_and_si512(_mm512_srli_epi16(u, 1), m3),
+                                        _mm512_and_si512(_mm512_srli_epi16(u, 2), m1));
+        code = _mm512_maskz_mov_epi8(ok, code);
+        const __m512i b = _mm512_madd_epi16(_mm512_maddubs_epi16(code, w14), w116);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(packed + 2 * g), _mm512_cvtepi32_epi8(b));
+        const uint64_t inv = ~(uint64_t)ok;
+        mask[g] = (uint32_t)inv;
+        mask[g + 1] = (uint32_t)(inv >> 32);
+    }
+    if (g < n_groups) pack_block_scalar(a + 32 * g, n_groups - g, packed + 2 * g, mask + g);
+}
+
+using PackFn = void (*)(const uint8_t *, int64_t, uint32_t *, uint32_t *);
+static PackFn choose_pack(int force) {
+    // force: 0 = best available, 1 = scalar, 2 = AVX2, 3 = AVX-512 (tests); unavailable -> nullptr
+    __builtin_cpu_init();
+    const bool has512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    const bool has2 = __builtin_cpu_supports("avx2");
+    switch (force) {
+    case 1: return pack_block_scalar;
+    case 2: return has2 ? pack_block_avx2 : nullptr;
+    case 3: return has512 ? pack_block_avx512 : nullptr;
+    default: return has512 ? pack_block_avx512 : has2 ? pack_block_avx2 : pack_block_scalar;
+    }
+}
+
+// ---- persistent worker pool --------------------------------------------------------------------------------
+// A job is a range of equal blocks; workers and the submitting thread draw block indices from one atomic
+// counter.  done[] lets a consumer wait for a PREFIX of the blocks (the ingest pipeline copies chunk c while
+// the pool packs chunk c+1).
+class Pool {
+public:
+    static Pool &get() {
+        static Pool p;
+        return p;
+    }
+    int size() const { return (int)workers_.size() + 1; }
+
+    struct Job {
+        const uint8_t *ascii;
+        uint32_t *packed, *mask;
+        int64_t n_groups, groups_per_block, n_blocks;
+        PackFn fn;
+        std::atomic<int64_t> next{0}, finished{0};
+        std::vector<std::atomic<uint8_t>> done;
+        explicit Job(int64_t blocks) : done((size_t)blocks) {
+            for (auto &d : done) d.store(0, std::memory_order_relaxed);
+        }
+        bool run_one() {
+            const int64_t b = next.fetch_add(1, std::memory_order_relaxed);
+            if (b >= n_blocks) return false;
+            const int64_t g0 = b * groups_per_block;
+            const int64_t ng = g0 + groups_per_block <= n_groups ? groups_per_block : n_groups - g0;
+            fn(ascii + 32 * g0, ng, packed + 2 * g0, mask + g0);
+            done[(size_t)b].store(1, std::memory_order_release);
+            finished.fetch_add(1, std::memory_order_release);
+            return true;
+        }
+    };
+
+    // start `job` on up to `threads` threads (workers only; the caller may help with job->run_one())
+    void start(Job *job, int threads) {
+        std::lock_guard<std::mutex> lk(mu_);
+        job_ = job;
+        want_ = threads - 1 < (int)workers_.size() ? (threads > 1 ? threads - 1 : 0) : (int)workers_.size();
+        generation_++;
+        active_ = want_;
+        cv_.notify_all();
+    }
+    // wait until every worker has left the job (the caller has seen all blocks finished)
+    void finish(Job *job) {
+        while (job->finished.load(std::memory_order_acquire) < job->n_blocks) {
+            if (!job->run_one()) std::this_thread::yield();
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        idle_cv_.wait(lk, [&] { return active_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    Pool() {
+        int n = 0;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);
+        if (n <= 0) n = (int)std::thread::hardware_concurrency();
+        if (n <= 0) n = 1;
+        if (n > 64) n = 64;
+        for (int i = 0; i < n - 1; i++) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            cv_.notify_all();
+        }
+        for (auto &t : workers_) t.join();
+    }
+    void loop(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            Job *job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                if (idx >= want_) continue;
+                job = job_;
+            }
+            while (job->run_one()) {
+            }
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--active_ == 0) idle_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, idle_cv_;
+    std::vector<std::thread> workers_;
+    Job *job_ = nullptr;
+    uint64_t generation_ = 0;
+    int want_ = 0, active_ = 0;
+    bool stop_ = false;
+};
+
+static std::mutex g_pack_mutex;  // one packing job at a time per process
+
+// Asynchronous packing job used by the ingest pipeline (sketch.cu): blocks are whole multiples of
+// `groups_per_block` 32-base groups; wait_prefix(b) returns once blocks [0, b) are packed.
+struct HostPackJob {
+    Pool::Job job;
+    std::unique_lock<std::mutex> lock;
+    HostPackJob(int64_t blocks) : job(blocks), lock(g_pack_mutex) {}
+};
+
+HostPackJob *host_pack_start(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
+                             int64_t bases_per_block, int threads) {
+    const int64_t n_groups = n_bases / 32, gpb = bases_per_block / 32;
+    const int64_t blocks = (n_groups + gpb - 1) / gpb;
+    auto *hp = new HostPackJob(blocks);
+    hp->job.ascii = h_ascii;
+    hp->job.packed = h_packed;
+    hp->job.mask = h_mask;
+    hp->job.n_groups = n_groups;
+    hp->job.groups_per_block = gpb;
+    hp->job.n_blocks = blocks;
+    hp->job.fn = choose_pack(0);
+    Pool &pool = Pool::get();
+    pool.start(&hp->job, threads > 0 ? threads : pool.size());
+    return hp;
+}
+void host_pack_wait_prefix(HostPackJob *hp, int64_t blocks) {
+    if (blocks > hp->job.n_blocks) blocks = hp->job.n_blocks;
+    for (int64_t b = 0; b < blocks; b++) {
+        while (!hp->job.done[(size_t)b].load(std::memory_order_acquire)) {
+            if (!hp->job.run_one()) std::this_thread::yield();  // help, then spin politely
+        }
+    }
+}
+void host_pack_finish(HostPackJob *hp) {
+    Pool::get().finish(&hp->job);
+    delete hp;
+}
+
+}  // namespace panib
+
+using namespace panib;
+
+extern "C" __attribute__((visibility("default"))) int panib_host_threads(void) { return Pool::get().size(); }
+
+extern "C" __attribute__((visibility("default"))) int panib_pack_host(const uint8_t *h_ascii, int64_t n_bases,
+                                                                      uint32_t *h_packed, uint32_t *h_mask,
+                                                                      int threads) {
+    if (n_bases < 0 || (n_bases & 31) || (n_bases && (!h_ascii || !h_packed || !h_mask))) {
+        set_error("panib_pack_host: n_bases=%lld must be a non-negative multiple of 32 with non-NULL buffers",
+                  (long long)n_bases);
+        return PANIB_E_ARG;
+    }
+    if (n_bases == 0) return PANIB_OK;
+    if (threads < 0) {  // tests: -1 scalar, -2 AVX2, -3 AVX-512 on the calling thread
+        PackFn fn = choose_pack(-threads);
+        if (!fn) {
+            set_error("panib_pack_host: this CPU lacks the requested instruction set");
+            return PANIB_E_ARG;
+        }
+        fn(h_ascii, n_bases / 32, h_packed, h_mask);
+        return PANIB_OK;
+    }
+    HostPackJob *hp = host_pack_start(h_ascii, n_bases, h_packed, h_mask, 1 << 18, threads);
+    host_pack_finish(hp);
+    return PANIB_OK;
+}

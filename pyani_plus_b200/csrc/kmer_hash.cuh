@@ -148,8 +148,14 @@ PANIB_HD U64 rotl(U64 x) {
 // (Measured and rejected: doing the 64-bit adds and the `>> 33` of fmix on the FMA pipe through
 // IMAD.WIDE with multipliers ptxas cannot fold -- 5-15 % SLOWER; IMAD.WIDE/IMAD.HI are not cheap.)
 PANIB_HD U64 add64(U64 a, U64 b) {
+#if defined(__CUDA_ARCH__)
+    U64 r;  // spelled as a carry chain: nvcc's own lowering of chained 64-bit adds wastes an IADD3
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi));
+    return r;
+#else
     const uint64_t r = to_u64(a) + to_u64(b);
     return U64{(uint32_t)r, (uint32_t)(r >> 32)};
+#endif
 }
 PANIB_HD U64 xor64(U64 a, U64 b) { return U64{a.lo ^ b.lo, a.hi ^ b.hi}; }
 PANIB_HD U64 xorshift33(U64 x) { return U64{x.lo ^ (x.hi >> 1), x.hi}; }  // x ^= x >> 33
@@ -169,16 +175,69 @@ PANIB_HD U64 mix_k2(U64 k2) {  // k2 *= c2; k2 = rotl(k2, 33); k2 *= c1
 
 // ---- MurmurHash3_x64_128 h1 of a K-byte key held as little-endian 32-bit words W[0..ceil(K/4)) ----
 // Bytes of W beyond K are ignored (masked here), so W may be a window of a longer byte string.
+//
+// The hash is returned UNFINISHED: h = xorshift33(m1) + xorshift33(m2) (the last step of both fmix64
+// and the final h1 += h2).  Only ~1/scaled of the k-mers survive `h <= max_hash`, so the hot loop
+// tests a one-sided filter on the high words (Partial::prefilter) and finishes the hash on the rare
+// path only: 2 instructions instead of 8 per k-mer.
+struct HashConsts {
+    uint32_t seed;
+    // Both "h = (rotl(h) + other) * 5 + c" steps are computed as 5 * (rotl(h) + other + c/5), with c/5 taken
+    // modulo 2^64 (5 is odd): one 64-bit 3-input add and one shift-add (LEA / LEA.HI.X), all on the ALU
+    // pipe, instead of a wide multiply-add chain on the FMA-heavy pipe that the 12 real multiplies saturate.
+    U64 a1;        // seed + 0x52dce729 / 5: block 0 adds h2 == seed, folded into the constant
+    U64 a2;        // 0x38495ab5 / 5
+    uint32_t thr;  // min(hi32(max_hash) + 1, 2^32 - 1)
+    uint64_t max_hash;
+};
+constexpr uint64_t kInv5 = 0xCCCCCCCCCCCCCCCDull;  // 5 * kInv5 == 1 (mod 2^64)
+static_assert(5ull * kInv5 == 1ull, "inverse of 5");
+PANIB_HD HashConsts make_hash_consts(uint32_t seed, uint64_t max_hash) {
+    const uint64_t a1 = (uint64_t)seed + 0x52dce729ull * kInv5;
+    const uint64_t a2 = 0x38495ab5ull * kInv5;
+    const uint32_t mh = (uint32_t)(max_hash >> 32);
+    return HashConsts{seed, U64{(uint32_t)a1, (uint32_t)(a1 >> 32)}, U64{(uint32_t)a2, (uint32_t)(a2 >> 32)},
+                      mh == 0xFFFFFFFFu ? mh : mh + 1u, max_hash};
+}
+
+struct Partial {
+    U64 m1, m2;
+    // Necessary condition for hash() <= max_hash.  hi32(hash) = m1.hi + m2.hi + carry, carry in {0,1},
+    // so hi32(hash) <= hi32(max_hash) implies (m1.hi + m2.hi + 1 mod 2^32) <= hi32(max_hash) + 1 whatever
+    // the carry is (with no carry the sum itself is <= hi32(max_hash) and the +1 cannot wrap).
+    PANIB_HD bool prefilter(const HashConsts &hc) const { return m1.hi + m2.hi + 1u <= hc.thr; }
+    PANIB_HD uint64_t hash() const { return to_u64(add64(xorshift33(m1), xorshift33(m2))); }
+};
+
+// 5 * (a + b + c): the 64-bit form lets nvcc emit IADD3 / IADD3.X and LEA / LEA.HI.X
+PANIB_HD U64 times5_sum(U64 a, U64 b, U64 c) {
+    const uint64_t t = to_u64(a) + to_u64(b) + to_u64(c);
+    const uint64_t r = (t << 2) + t;
+    return U64{(uint32_t)r, (uint32_t)(r >> 32)};
+}
+PANIB_HD U64 times5_sum(U64 a, U64 c) {
+    const uint64_t t = to_u64(a) + to_u64(c);
+    const uint64_t r = (t << 2) + t;
+    return U64{(uint32_t)r, (uint32_t)(r >> 32)};
+}
+PANIB_HD U64 fmix_head(U64 k) {  // fmix64 without its last xorshift
+    k = xorshift33(k);
+    k = mul_const<0xff51afd7ed558ccdULL>(k);
+    k = xorshift33(k);
+    return mul_const<0xc4ceb9fe1a85ec53ULL>(k);
+}
+
 template <int K>
-PANIB_HD uint64_t murmur_words(const uint32_t *W, uint32_t seed) {
-    U64 h1{seed, 0u}, h2{seed, 0u};
+PANIB_HD Partial murmur_words(const uint32_t *W, const HashConsts &hc) {
+    U64 h1{hc.seed, 0u}, h2{hc.seed, 0u};
     constexpr int nblocks = K / 16;
 #pragma unroll
     for (int i = 0; i < nblocks; i++) {
         h1 = xor64(h1, mix_k1(U64{W[4 * i], W[4 * i + 1]}));
-        h1 = mul5_add<0x52dce729u>(add64(rotl<27>(h1), h2));
+        if (i == 0) h1 = times5_sum(rotl<27>(h1), hc.a1);  // h2 is still the seed
+        else h1 = mul5_add<0x52dce729u>(add64(rotl<27>(h1), h2));
         h2 = xor64(h2, mix_k2(U64{W[4 * i + 2], W[4 * i + 3]}));
-        h2 = mul5_add<0x38495ab5u>(add64(rotl<31>(h2), h1));
+        h2 = times5_sum(rotl<31>(h2), h1, hc.a2);
     }
     constexpr int tail = K & 15;
     constexpr int tb = 4 * nblocks;  // first tail word
@@ -202,20 +261,30 @@ PANIB_HD uint64_t murmur_words(const uint32_t *W, uint32_t seed) {
     h2.lo ^= (uint32_t)K;
     h1 = add64(h1, h2);
     h2 = add64(h2, h1);
-    h1 = fmix(h1);
-    h2 = fmix(h2);
-    return to_u64(add64(h1, h2));
+    return Partial{fmix_head(h1), fmix_head(h2)};
 }
 
 // ---- geometry of one thread's span for k-mer size K ------------------------------------------
 template <int K>
 struct Geom {
     static_assert(K >= 1 && K <= 32, "register-resident kernel handles 1 <= K <= 32");
+    static_assert(kKmersPerThread == 16, "the tile expansion below assumes 16 k-mers (64 bases) per thread");
     static constexpr int SPAN = 4 * (kKmersPerThread - 1) + K;  // bases touched by one thread
     static constexpr int NX = (2 * SPAN + 6 + 31) / 32;         // packed words (incl. 0..6 bits of alignment)
     static constexpr int NA = (SPAN + 3) / 4;                   // ASCII words per strand
     static constexpr int NWD = (K + 3) / 4;                     // ASCII words per k-mer
-    static constexpr int RCSHIFT = 2 * (16 * NX - SPAN);        // bits to drop after pair-reversal
+    static constexpr int NU = kThreadsK1 / 4;                   // 64-base blocks per CTA tile
+    static constexpr int NI = kCtaTile / 16;                    // packed words per CTA tile
+    static constexpr int ITEMS = NI + 2;                        // ... expanded per tile (incl. the K-1 halo)
+    // reverse strand: the tile (kCtaTile + K bases) is read back to front as the stream
+    //   RCm[x] = comp(T[kCtaTile + K - 2 - x]),
+    // in which the reverse complement of the k-mer at tile position p = 64u + a + 4j starts at
+    // 4 * (kCtaTile/4 - 1 - 16u - j) + (3 - a): word-aligned in the copy shifted by 3 - a bytes, and
+    // 4-byte steps apart for consecutive j, exactly like the forward strand.  Packed word v of RCm is the
+    // reverse complement of the 16 tile bases starting at 16 * (NI - v) + K - 17.
+    static constexpr int RC_D = K - 21;  // first base of the 20-base group of item v: 16 * (NI - v) + RC_D
+    static constexpr int RC_DQ = RC_D >= 0 ? RC_D / 16 : -((15 - RC_D) / 16);  // floor(RC_D / 16)
+    static constexpr int RC_DR = RC_D - 16 * RC_DQ;                            // 0..15
 };
 
 // 16 bases (one packed word) -> 4 ASCII words.  LUT byte c = ASCII of code c.
@@ -233,6 +302,12 @@ PANIB_HD void expand16(uint32_t x, uint32_t *out4) {
     out4[1] = prmt(lut, 0u, lo >> 16);
     out4[2] = prmt(lut, 0u, hi);
     out4[3] = prmt(lut, 0u, hi >> 16);
+}
+// 4 bases (the low 8 bits of x; the rest must be zero) -> 1 ASCII word
+PANIB_HD uint32_t expand4(uint32_t x) {
+    x = (x | (x << 4)) & 0x0F0Fu;
+    x = (x | (x << 2)) & 0x3333u;
+    return prmt(0x54474341u, 0u, x);
 }
 
 // reverse the order of the 16 2-bit fields of a word and complement them
@@ -258,101 +333,226 @@ PANIB_HD uint64_t window(const uint32_t *X, int off) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-// Hash the 16 k-mers of thread (u, a) of a tile.
-//   sp   : packed words of the tile (word 0 bit 0 = tile position 0), kTileWords valid words
-//   sm   : validity-mask words of the tile (bit set = invalid), kTileMaskWords valid words
-//   blk  : this thread's private scratch of 2*kBlkWords words (shared memory on the GPU, words of
-//          consecutive threads kBlkWords apart: odd stride = bank-conflict free)
-//   emit : callable(uint64_t h) invoked for every VALID k-mer (caller applies the max_hash test)
-// DIRTY=false skips the per-k-mer validity test (caller guarantees the tile has no invalid base).
+// ================================================================================================
+// K1 works on a CTA tile in two phases.
 //
-// The ASCII form of the thread's span (both strands) is written ONCE to the thread's scratch block;
-// k-mer j then reads its NWD words from `fwd ? blk + j : blk + kBlkWords + 15 - j`: the canonical
-// choice costs one address select and the words arrive through the (otherwise idle) load/store pipe,
-// instead of NWD SEL instructions on the ALU pipe, which is the pipe that limits K1.
-constexpr int kBlkWords = 23;  // ASCII words per strand of a span: ceil((60 + 32) / 4), odd on purpose
+// Phase A (tile_expand_item, cooperative): the ASCII form of both strands of the tile is produced ONCE
+// per CTA -- item t = packed word t of the tile (16 bases) is expanded by one thread, shifted by 0..3
+// bytes with PRMT, and stored straight into the private scratch blocks of the threads that will hash
+// it -- instead of every thread expanding its own 91-base span (each base 4x per strand).
+//
+// Phase B (hash_thread_kmers): thread (u, a) hashes its 16 k-mers.  Its scratch block holds the ASCII
+// words of its span for both strands, so k-mer j reads its NWD words from
+// `fwd ? blk + j : blk + kBlkWords + 15 - j`: the canonical choice costs one address select and the
+// words arrive through the otherwise idle load/store pipe.
+//
+// Scratch layout (kBlkWords words per strand and thread, element-major): element e of thread tid lives
+// at scratch[e * nthreads + tid] (forward) / scratch[(kBlkWords + e) * nthreads + tid] (reverse): a
+// warp's accesses to one element are 32 consecutive words whatever strand each lane picks.
+//   forward element e of thread (u, a) = tile bytes   [64u + a + 4e, +4)  = word 16u + e of the copy shifted by a
+//   reverse element e of thread (u, a) = RCm bytes [64(NU-1-u) + (3-a) + 4e, +4) = word 16(NU-1-u) + e of the
+//                                        copy shifted by 3 - a
+// so word w of a shifted copy goes to block w >> 4 at element w & 15 and, because spans overlap by
+// NA - 16 words, also to the neighbouring block at element (w & 15) + 16 when that is < NA.
+// ================================================================================================
+constexpr int kBlkWords = 23;  // ASCII words per strand of a span: ceil((60 + 32) / 4)
+constexpr int kSpLead = 4;     // readable words in front of the staged packed tile (content irrelevant)
 
-template <int K, bool DIRTY, class Emit>
-PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *sm, uint32_t *blk, int blk_stride, int u, int a,
-                                uint32_t seed, Emit &&emit) {
+// packed word v of the reverse stream RCm (reverse complement of the 16 tile bases from 16(NI - v) + K - 17)
+// and, in g8, the 4 tile bases in front of them (they become the first 4 bases of word v + 1)
+template <int K>
+PANIB_HD uint32_t rc_packed_word(const uint32_t *sp, int v, uint32_t &g8) {
     using G_ = Geom<K>;
-    constexpr int NX = G_::NX, NA = G_::NA, NWD = G_::NWD;
-    static_assert(NA <= kBlkWords, "scratch block too small");
-    const uint32_t *src = sp + (kKmersPerThread / 4) * u;  // span starts at tile position 4*KPT*u + a
-    uint32_t X[NX];
-#pragma unroll
-    for (int w = 0; w < NX - 1; w++) X[w] = shf_r(src[w], src[w + 1], 2 * a);
-    X[NX - 1] = src[NX - 1] >> (2 * a);
+    const uint32_t *s = sp + (G_::NI - v + G_::RC_DQ);
+    constexpr int sh = 2 * G_::RC_DR;
+    uint32_t g32;
+    if constexpr (sh == 0) g8 = s[0] & 0xFFu;
+    else g8 = shf_r(s[0], s[1], sh) & 0xFFu;
+    if constexpr (sh + 8 < 32) g32 = shf_r(s[0], s[1], sh + 8);
+    else if constexpr (sh + 8 == 32) g32 = s[1];
+    else g32 = shf_r(s[1], s[2], sh + 8 - 32);
+    return revcomp16(g32);
+}
 
-    // packed reverse complement of the span, LSB-first: Xr base p = comp(X base SPAN-1-p)
-    uint32_t Z[NX + 2];
+// Phase A for item t (0 <= t < Geom<K>::NI; the halo items are tile_expand_halo's).  sp[-1] .. sp[NI + 2] must be readable; rcp receives
+// packed word t of the reverse stream (used by phase B for the canonical comparison).
+// In round r the lane stores the copy shifted by (t + r) & 3 bytes: the four lanes that share a block
+// then write four different threads' slots, which makes every store instruction of a warp hit 32
+// different banks.
+template <int K>
+PANIB_HD void tile_expand_item(const uint32_t *sp, uint32_t *rcp, uint32_t *scratch, int nthreads, int t) {
+    using G_ = Geom<K>;
+    constexpr int NA = G_::NA;
+    static_assert(NA <= kBlkWords && NA - 16 <= 7, "scratch block too small");
+    const int up = t >> 2, m = t & 3;
+    uint32_t sel[4];
+    int ar[4];
 #pragma unroll
-    for (int w = 0; w < NX; w++) Z[w] = revcomp16(X[NX - 1 - w]);
-    Z[NX] = 0u;
-    Z[NX + 1] = 0u;
-    uint32_t Xr[NX];
-    constexpr int wo = G_::RCSHIFT >> 5, sh = G_::RCSHIFT & 31;
-#pragma unroll
-    for (int w = 0; w < NX; w++) {
-        uint32_t l = (w + wo < NX) ? Z[w + wo] : 0u;
-        uint32_t h = (w + wo + 1 < NX) ? Z[w + wo + 1] : 0u;
-        Xr[w] = sh ? shf_r(l, h, sh) : l;
+    for (int r = 0; r < 4; r++) {
+        ar[r] = (m + r) & 3;
+        sel[r] = 0x3210u + 0x1111u * (uint32_t)ar[r];
     }
-
-    // ASCII expansion of both strands, each base once per thread, straight into the scratch block
-    // (element e of the block lives at blk[e * blk_stride]: stride 1 on the host, blockDim on the GPU
-    // so that a warp's accesses to the same element are consecutive words)
-    uint32_t *fw = blk, *rv = blk + kBlkWords * blk_stride;
+    const bool nb_ok = up >= 1;
+    uint32_t E[5];
+    // ---- forward strand: tile bases [16t, 16t + 20)
+    expand16(sp[t], E);
+    E[4] = expand4(sp[t + 1] & 0xFFu);
+    {
+        uint32_t *p0 = scratch + (4 * m) * nthreads + 4 * up;
 #pragma unroll
-    for (int w = 0; w < NX; w++) {
-        if (4 * w < NA) {
-            uint32_t e[4];
-            expand16(X[w], e);
+        for (int i = 0; i < 4; i++) {
+            const bool sec = nb_ok && (4 * m + i + 16 < NA);
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (4 * w + i < NA) fw[(4 * w + i) * blk_stride] = e[i];
-            expand16(Xr[w], e);
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (4 * w + i < NA) rv[(4 * w + i) * blk_stride] = e[i];
-        }
-    }
-
-    // PANIB_K1_GROUP k-mers are hashed back to back before any of them is offered to the table: the
-    // conditional insert (a call) ends a basic block, and inside one block the compiler can interleave
-    // the independent MurmurHash3 chains of the group.  Measured neutral on B200 (groups of 1/2/4/8:
-    // 2.68 / 2.68 / 2.71 / 2.68 ms at config 2 -- the kernel is bound by pipe throughput, not by
-    // dependency stalls), so the default stays 1.
-#ifndef PANIB_K1_GROUP
-#define PANIB_K1_GROUP 1
-#endif
-    constexpr int GRP = PANIB_K1_GROUP;
-    static_assert(kKmersPerThread % GRP == 0, "group size must divide the k-mers per thread");
-#pragma unroll
-    for (int j0 = 0; j0 < kKmersPerThread; j0 += GRP) {
-        uint64_t h[GRP];
-        bool valid[GRP];
-#pragma unroll
-        for (int jj = 0; jj < GRP; jj++) {
-            const int j = j0 + jj;
-            valid[jj] = true;
-            if (DIRTY) {
-                const int pos = 4 * kKmersPerThread * u + a + 4 * j;
-                uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
-                if (K < 32) mw &= (1u << (K & 31)) - 1u;
-                valid[jj] = (mw == 0u);
+            for (int r = 0; r < 4; r++) {
+                const uint32_t v = prmt(E[i], E[i + 1], sel[r]);
+                uint32_t *p = p0 + i * nthreads + ar[r];
+                p[0] = v;
+                if (sec) p[16 * nthreads - 4] = v;
             }
-            const uint64_t F = window<K, NX>(X, 8 * j);
-            const uint64_t R = window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
-            const uint32_t *words = F < R ? fw + j * blk_stride : rv + (kKmersPerThread - 1 - j) * blk_stride;
-            uint32_t W[NWD];
-#pragma unroll
-            for (int i = 0; i < NWD; i++) W[i] = words[i * blk_stride];
-            h[jj] = murmur_words<K>(W, seed);
         }
+    }
+    // ---- reverse strand: RCm positions [16t, 16t + 20) = reverse complement of tile bases
+    //      [16(NI - t) + RC_D, +20), of which the last 16 make packed word t of RCm
+    {
+        uint32_t g8;
+        const uint32_t rcw = rc_packed_word<K>(sp, t, g8);
+        rcp[t] = rcw;
+        expand16(rcw, E);
+        E[4] = expand4(revcomp16(g8 << 24) & 0xFFu);
+        uint32_t *p0 = scratch + (kBlkWords + 4 * m) * nthreads + 4 * (G_::NU - 1 - up) + 3;
 #pragma unroll
-        for (int jj = 0; jj < GRP; jj++)
-            if (!DIRTY || valid[jj]) emit(h[jj]);
+        for (int i = 0; i < 4; i++) {
+            const bool sec = nb_ok && (4 * m + i + 16 < NA);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t v = prmt(E[i], E[i + 1], sel[r]);
+                uint32_t *p = p0 + i * nthreads - ar[r];
+                p[0] = v;
+                if (sec) p[16 * nthreads + 4] = v;
+            }
+        }
+    }
+}
+
+// Phase A, halo: the K-1 bases behind the tile (items NI, NI+1) only feed the overlap elements 16..NA-1 of
+// the last forward block (u = NU-1) and of the last reverse block (u = 0).  ONE warp does this, one
+// (strand, word, pair of shifts) per lane, so that no warp is a whole item behind the others at the
+// barrier.  Lanes 14 / 15 (idle otherwise) store the two packed reverse words the last block compares.
+template <int K>
+PANIB_HD void tile_expand_halo(const uint32_t *sp, uint32_t *rcp, uint32_t *scratch, int nthreads, int lane) {
+    using G_ = Geom<K>;
+    constexpr int NA = G_::NA;
+    const int strand = lane >> 4, hw = (lane >> 1) & 7, ap = lane & 1;
+    if (hw < NA - 16) {
+        uint32_t g16;
+        if (strand == 0) {  // tile bases [kCtaTile + 4hw, +8)
+            const uint32_t *s = sp + G_::NI + (hw >> 2);
+            g16 = shf_r(s[0], s[1], 8u * (uint32_t)(hw & 3)) & 0xFFFFu;
+        } else {  // RCm positions [kCtaTile + 4hw, +8) = reverse complement of tile bases [K - 9 - 4hw, +8)
+            const int tb = K - 9 - 4 * hw;
+            const uint32_t *s = sp + (tb >> 4);  // arithmetic shift: the lead-in words cover tb < 0
+            g16 = revcomp16(shf_r(s[0], s[1], 2u * (uint32_t)(tb & 15)) << 16) & 0xFFFFu;
+        }
+        const uint32_t e0 = expand4(g16 & 0xFFu), e1 = expand4(g16 >> 8);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int sft = 2 * ap + q;  // copy shifted by sft bytes
+            const uint32_t v = prmt(e0, e1, 0x3210u + 0x1111u * (uint32_t)sft);
+            if (strand == 0) scratch[(16 + hw) * nthreads + 4 * (G_::NU - 1) + sft] = v;
+            else scratch[(kBlkWords + 16 + hw) * nthreads + 3 - sft] = v;
+        }
+    } else if (strand == 0) {
+        uint32_t g8;
+        rcp[G_::NI + ap] = rc_packed_word<K>(sp, G_::NI + ap, g8);
+    }
+}
+
+// validity of the 16 k-mers of thread (u, a): bit j set = no invalid base in k-mer j.  sm = validity
+// mask words of the tile (bit set = invalid).  Only called for tiles that hold an invalid base.
+template <int K>
+PANIB_HD uint32_t thread_valid_mask(const uint32_t *sm, int u, int a) {
+    uint32_t vm = 0;
+#pragma unroll 1
+    for (int j = 0; j < kKmersPerThread; j++) {
+        const int pos = 4 * kKmersPerThread * u + a + 4 * j;
+        uint32_t mw = shf_r(sm[pos >> 5], sm[(pos >> 5) + 1], pos & 31);
+        if (K < 32) mw &= (1u << (K & 31)) - 1u;
+        vm |= (mw == 0u ? 1u : 0u) << j;
+    }
+    return vm;
+}
+
+// 64 bits of a packed multiword value starting at (compile-time) bit offset `off`, no masking
+template <int NXW>
+PANIB_HD void window64(const uint32_t *X, int off, uint32_t &lo, uint32_t &hi) {
+    const int w = off >> 5, s = off & 31;
+    if (s == 0) {
+        lo = X[w];
+        hi = (w + 1 < NXW) ? X[w + 1] : 0u;
+    } else {
+        lo = shf_r(X[w], (w + 1 < NXW) ? X[w + 1] : 0u, s);
+        hi = shf_r((w + 1 < NXW) ? X[w + 1] : 0u, (w + 2 < NXW) ? X[w + 2] : 0u, s);
+    }
+}
+
+// Phase B: hash the 16 k-mers of thread (u, a) of a tile.
+//   sp    : packed words of the tile (word 0 bit 0 = tile position 0); sp[-1] readable
+//   rcp   : packed words of the reverse stream RCm (written by phase A); rcp[-1] readable
+//   blk   : this thread's scratch (scratch + tid), stride blk_stride between elements
+//   vmask : bit j set = k-mer j is valid (0xFFFF for a tile without invalid bases)
+//   emit  : callable(const Partial &) invoked for every valid k-mer that passes the prefilter
+//
+// Canonical choice (fwd < revcomp) on the packed form: with LSB-first packing it is F < R for the 2K-bit
+// windows of the packed span and of the packed reverse stream.  For K = 31 / 32 the spans are loaded
+// 32 - K bases early, so that k-mer j's window sits in bits [8j, 8j + 64) and is compared whole: the low
+// 2 bits (K = 31) hold a neighbouring base on both sides, which could only decide a comparison whose 31
+// real bases tie -- impossible, an odd-length k-mer is never its own reverse complement.  Windows of
+// every fourth k-mer are register-aligned.  Other K use masked windows.
+template <int K, class Emit>
+PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *rcp, const uint32_t *blk, int blk_stride,
+                                int u, int a, uint32_t vmask, const HashConsts &hc, Emit &&emit) {
+    using G_ = Geom<K>;
+    constexpr int NX = G_::NX, NWD = G_::NWD;
+    constexpr bool WHOLE = (K == 31 || K == 32);  // 64-bit windows without masks
+    constexpr int EARLY = WHOLE ? 32 - K : 0;     // bases the spans start early
+    uint32_t X[NX], Xr[NX];
+    {
+        // forward span from tile position 64u + a - EARLY, reverse span from RCm position
+        // 64(NU-1-u) + 3 - a - EARLY (word index and shift computed per lane)
+        const int pf = 4 * kKmersPerThread * u + a - EARLY;
+        const int pr = 4 * kKmersPerThread * (G_::NU - 1 - u) + 3 - a - EARLY;
+        const uint32_t *src = sp + (pf >> 4);  // arithmetic shift: -1 >> 4 = -1
+        const uint32_t *srcr = rcp + (pr >> 4);
+        const uint32_t sf = 2u * (uint32_t)(pf & 15), sr = 2u * (uint32_t)(pr & 15);
+#pragma unroll
+        for (int w = 0; w < NX; w++) {
+            X[w] = shf_r(src[w], src[w + 1], sf);
+            Xr[w] = shf_r(srcr[w], srcr[w + 1], sr);
+        }
+    }
+    const uint32_t *fw = blk;
+    constexpr int RV0 = kBlkWords + kKmersPerThread - 1;  // reverse element of k-mer j: RV0 - j (+ i)
+#pragma unroll
+    for (int j = 0; j < kKmersPerThread; j++) {
+        bool lt;
+        if constexpr (WHOLE) {
+            uint32_t flo, fhi, rlo, rhi;
+            window64<NX>(X, 8 * j, flo, fhi);
+            window64<NX>(Xr, 8 * (kKmersPerThread - 1 - j), rlo, rhi);
+            lt = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
+        } else {
+            lt = window<K, NX>(X, 8 * j) < window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
+        }
+        // forward words at element j + i, reverse words at RV0 - j + i: one select, one add
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(
+            reinterpret_cast<const char *>(fw) + (lt ? 0 : (RV0 - 2 * j) * blk_stride * 4));
+        uint32_t W[NWD];
+#pragma unroll
+        for (int i = 0; i < NWD; i++) W[i] = words[(j + i) * blk_stride];
+        const Partial p = murmur_words<K>(W, hc);
+        if (p.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
+            if (vmask & (1u << j)) emit(p);
+        }
     }
 }
 

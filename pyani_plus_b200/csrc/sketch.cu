@@ -61,7 +61,28 @@ __device__ __noinline__ void table_insert(uint64_t *__restrict__ row, int nb, ui
     atomicOr(status, PANIB_ST_BUCKET_OVERFLOW);
 }
 
+// what phase B needs to insert a survivor: per-tile genome data, looked up by ONE thread per tile and
+// parked in shared memory (the other 255 threads read it on the rare survivor path only)
+struct GenomeSlot {
+    uint64_t *row;
+    uint64_t bmul;
+    int32_t *flag;
+    int nb;
+};
+
 struct EmitToTable {
+    const GenomeSlot *slot;  // shared memory
+    uint64_t max_hash;
+    int32_t *status;
+    // survivor path of the fast kernel: finish the hash, exact test, insert
+    __device__ __forceinline__ void operator()(const Partial &p) const {
+        const uint64_t h = p.hash();
+        if (h <= max_hash) table_insert(slot->row, slot->nb, slot->bmul, h, slot->flag, status);
+    }
+};
+
+// generic kernel: complete hash, genome data in registers
+struct EmitHash {
     uint64_t *row;
     int nb;
     uint64_t bmul;
@@ -69,37 +90,11 @@ struct EmitToTable {
     int32_t *flag;
     int32_t *status;
     __device__ __forceinline__ void operator()(uint64_t h) const {
-        // keep iff 0 < h <= max_hash
-        if (h <= max_hash) table_insert(row, nb, bmul, h, flag, status);
+        if (h <= max_hash) table_insert(row, nb, bmul, h, flag, status);  // keep iff 0 < h <= max_hash
     }
 };
 
-// Experimental (PANIB_K1_QUEUE = queue slots, default 0 = off): survivors are parked in a small
-// shared-memory queue while the tile is hashed and inserted by all threads together after the tile, so
-// that the hot loop never waits for a global atomicCAS in a mostly idle warp.  A full queue falls back to
-// the direct insert.  Measured on B200 with 256 slots: scaled=100 (config 5) 69.6 -> 59.7 ms (+17 %
-// Gbp/s), scaled=1000 (config 2) 2.678 -> 2.738 ms (-2 %: one survivor per 1000 k-mers does not pay for
-// the extra shared atomics and the drain).  Passes the fixture / scaled=1 / scaled=50 / edge-shape /
-// config-2 parity tests; not yet run under racecheck, hence still off.  Next step: compile both forms
-// and pick by scaled at launch (queue below scaled ~ 300).
-#ifndef PANIB_K1_QUEUE
-#define PANIB_K1_QUEUE 0
-#endif
-struct EmitToQueue {
-    EmitToTable direct;
-    uint64_t *queue;
-    int *count;
-    __device__ __forceinline__ void operator()(uint64_t h) const {
-        if (h <= direct.max_hash) {
-            const int slot = atomicAdd(count, 1);
-            if (slot < PANIB_K1_QUEUE) queue[slot] = h;
-            else table_insert(direct.row, direct.nb, direct.bmul, h, direct.flag, direct.status);
-        }
-    }
-};
-
-// genome owning `tile`: largest g with tile_off[g] <= tile (all threads compute it redundantly; the
-// loads are uniform and L1-resident).  `g` is the previous answer, tried first.
+// genome owning `tile`: largest g with tile_off[g] <= tile.  `g` is the previous answer, tried first.
 __device__ __forceinline__ int find_genome(const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile,
                                            int g) {
     if (tile >= __ldg(tile_off + g) && tile < __ldg(tile_off + g + 1)) return g;
@@ -120,104 +115,90 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// K1, register-resident form for compile-time K <= 32 (see kmer_hash.cuh for the thread geometry).
-// Persistent CTAs (grid = SMs x resident CTAs) walk the tiles with stride gridDim.x; the next tile
-// is prefetched with cp.async into the other half of a double buffer while the current one is
-// hashed.  __launch_bounds__(256, 4) keeps the kernel at <= 64 registers (lazy ASCII expansion in
-// kmer_hash.cuh makes that spill-free): K1 is bound by the ALU pipe, and 32 resident warps per SM
-// measured 8 % faster than 16 (ncu: profiles/).  A warp-private-tile variant without CTA barriers
-// was measured 6 % SLOWER (its warps drift apart and the 40 KB unrolled body thrashes the
-// instruction cache), so tiles stay CTA-wide.
+// K1, fast form for compile-time K <= 32 (kmer_hash.cuh describes the two phases and the thread
+// geometry).  Persistent CTAs (grid = SMs x resident CTAs) draw CTA tiles from a ticket counter; the
+// packed tile after the current one is prefetched with cp.async into the other half of a double buffer.
+// Per tile: barrier (tile landed, scratch free) -> phase A, cooperative ASCII expansion of both strands
+// into the threads' scratch blocks -> barrier -> phase B, 16 k-mers per thread.
+// __launch_bounds__(256, 4): 64 registers, 32 resident warps per SM (K1 is bound by issue slots and the
+// two integer pipes; 32 warps measured 8 % faster than 16).
 // ------------------------------------------------------------------------------------------------
 #ifndef PANIB_K1_MINBLOCKS
 #define PANIB_K1_MINBLOCKS 4
 #endif
+constexpr int kSpStage = kSpLead + kTileWords;  // lead-in + tile + halo words of one staging buffer
+
 template <int K>
 __global__ void __launch_bounds__(kThreadsK1, PANIB_K1_MINBLOCKS)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
                    const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
-                   uint32_t seed, uint64_t max_hash, const int32_t *__restrict__ nb,
+                   const HashConsts hc, const int32_t *__restrict__ nb,
                    const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
                    int32_t *flags, int32_t *status, uint32_t *ticket) {
-    // stream tiles [tile_begin, n_tiles) = CTA tiles [tile_begin*S, n_tiles*S), S = kTileBases/kCtaTile:
-    // persistent CTAs, double buffer, two barriers per CTA tile
-    __shared__ __align__(16) uint32_t sp[2][kTileWords];
+    // hc arrives as a kernel parameter (computed on the host): its 64-bit constants then sit in uniform
+    // registers and feed the 3-input adds directly, instead of being folded into immediates one at a time
+    using G_ = Geom<K>;
+    const uint64_t max_hash = hc.max_hash;
+    __shared__ __align__(16) uint32_t sp_[2][kSpStage];
     __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
-    // per-thread ASCII scratch, element-major: element e of thread t at blk[e * kThreadsK1 + t]
-    extern __shared__ uint32_t blk_all[];  // kK1DynSmem bytes
-    uint32_t *blk = blk_all + threadIdx.x;
+    __shared__ __align__(16) uint32_t rcp_[kSpStage];
+    __shared__ GenomeSlot s_slot;
+    __shared__ int64_t s_next;
+    // per-thread ASCII scratch, element-major: element e of thread t at scratch[e * kThreadsK1 + t]
+    extern __shared__ uint32_t scratch[];  // kK1DynSmem bytes
     constexpr int S = kTileBases / kCtaTile;
     n_tiles *= S;
     int64_t tile = tile_begin * S + blockIdx.x;
     if (tile >= n_tiles) return;
+    const int tid = threadIdx.x;
     auto prefetch = [&](int64_t t, int b) {
         const uint32_t *gp = packed + t * (kCtaTile / 16);
         const uint32_t *gm = mask + t * (kCtaTile / 32);
-        const int x = threadIdx.x;
-        if (x < kTileWords / 4) cp_async16(sp[b] + 4 * x, gp + 4 * x);
-        else if (x < kTileWords / 4 + kTileMaskWords / 4)
-            cp_async16(sm[b] + 4 * (x - kTileWords / 4), gm + 4 * (x - kTileWords / 4));
+        if (tid < kTileWords / 4) cp_async16(sp_[b] + kSpLead + 4 * tid, gp + 4 * tid);
+        else if (tid < kTileWords / 4 + kTileMaskWords / 4)
+            cp_async16(sm[b] + 4 * (tid - kTileWords / 4), gm + 4 * (tid - kTileWords / 4));
         cp_async_commit();
     };
     prefetch(tile, 0);
+    if (tid < 2 * kSpLead) sp_[tid / kSpLead][tid % kSpLead] = 0u;  // lead-in words: read, never used
+    else if (tid < 3 * kSpLead) rcp_[tid - 2 * kSpLead] = 0u;
+    uint32_t *const rcp = rcp_ + kSpLead;
     // Tiles after a CTA's first come from a ticket counter (`ticket`, zeroed by the host before the
     // launch) rather than from a fixed stride: the warp scheduler favours some resident CTAs, so with
-    // equal fixed shares the favoured CTAs leave early and the SM ends the launch under-occupied
-    // (ncu: 24 of 32 warps active on average).  Thread 0 draws the ticket for the tile after next while
-    // the current tile is hashed; the barrier that ends the tile publishes it.
-    __shared__ int64_t s_next;
-#if PANIB_K1_QUEUE > 0
-    __shared__ uint64_t s_queue[PANIB_K1_QUEUE];
-    __shared__ int s_qn;
-#endif
+    // equal fixed shares the favoured CTAs leave early and the SM ends the launch under-occupied.
+    // Thread 0 draws the ticket for the tile after next while the current tile is expanded.
     const int64_t dyn_base = tile_begin * S + gridDim.x;
-    if (ticket) {
-        if (threadIdx.x == 0) s_next = dyn_base + atomicAdd(ticket, 1u);
-        __syncthreads();
-    }
+    if (ticket && tid == 0) s_next = dyn_base + atomicAdd(ticket, 1u);
+    __syncthreads();
     int64_t next = ticket ? s_next : tile + gridDim.x;
-    const int u = threadIdx.x >> 2, a = threadIdx.x & 3;
+    const int u = tid >> 2, a = tid & 3;
+    const EmitToTable emit{&s_slot, max_hash, status};
     int g = 0;
     for (int it = 0; tile < n_tiles; ++it) {
         const int cur = it & 1;
-        if (next < n_tiles) {
-            prefetch(next, cur ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        cp_async_wait<0>();
+        __syncthreads();  // tile `cur` has landed; every thread is done with the previous tile's scratch
+        if (next < n_tiles) prefetch(next, cur ^ 1);
+        const uint32_t *sp = sp_[cur] + kSpLead;
+        // one thread per job: next ticket (warp 0), this tile's genome slot (warp 1)
         uint32_t drawn = 0;
-        if (ticket && threadIdx.x == 0 && next < n_tiles) drawn = atomicAdd(ticket, 1u);
-#if PANIB_K1_QUEUE > 0
-        if (threadIdx.x == 0) s_qn = 0;  // every thread has drained the previous tile before the barrier above
-#endif
-        const uint32_t m = threadIdx.x < kTileMaskWords ? sm[cur][threadIdx.x] : 0u;
-        const bool dirty = __syncthreads_or(m != 0u) != 0;
-        g = find_genome(tile_off, n_genomes, tile / S, g);
-        EmitToTable to_table{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g,
-                             status};
-#if PANIB_K1_QUEUE > 0
-        EmitToQueue emit{to_table, s_queue, &s_qn};
-#else
-        EmitToTable emit = to_table;
-#endif
-        if (!dirty) {
-            hash_thread_kmers<K, false>(sp[cur], sm[cur], blk, kThreadsK1, u, a, seed, emit);
-        } else {
-            hash_thread_kmers<K, true>(sp[cur], sm[cur], blk, kThreadsK1, u, a, seed, emit);
+        if (tid == 0) {
+            if (ticket && next < n_tiles) drawn = atomicAdd(ticket, 1u);
+            s_next = ticket ? (next < n_tiles ? dyn_base + drawn : n_tiles) : next + gridDim.x;
+        } else if (tid == 32) {
+            g = find_genome(tile_off, n_genomes, tile / S, g);
+            s_slot = GenomeSlot{table + (size_t)g * row_stride, __ldg(bmul + g), flags + g, __ldg(nb + g)};
         }
-        if (ticket && threadIdx.x == 0) s_next = next < n_tiles ? dyn_base + drawn : n_tiles;
-        __syncthreads();
-#if PANIB_K1_QUEUE > 0
-        {
-            const int queued = s_qn < PANIB_K1_QUEUE ? s_qn : PANIB_K1_QUEUE;
-            for (int i = threadIdx.x; i < queued; i += kThreadsK1)
-                table_insert(to_table.row, to_table.nb, to_table.bmul, s_queue[i], to_table.flag, to_table.status);
-        }
-#endif
+        // phase A: items 0..255 one per thread, the halo by warp 2
+        tile_expand_item<K>(sp, rcp, scratch, kThreadsK1, tid);
+        if ((tid >> 5) == 2) tile_expand_halo<K>(sp, rcp, scratch, kThreadsK1, tid & 31);
+        const uint32_t mw = tid < kTileMaskWords ? sm[cur][tid] : 0u;
+        const bool dirty = __syncthreads_or(mw != 0u) != 0;
+        // phase B
+        const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
+        hash_thread_kmers<K>(sp, rcp, scratch + tid, kThreadsK1, u, a, vmask, hc, emit);
         tile = next;
-        next = ticket ? s_next : next + gridDim.x;
+        next = s_next;  // written before the barrier above, overwritten after the next one
     }
 }
 
@@ -257,7 +238,7 @@ sketch_hash_generic_kernel(const uint32_t *__restrict__ packed, const uint32_t *
     if (tile >= n_tiles) return;
     stage_tile<kGenWords, kGenMask>(packed, mask, tile, sp, sm);
     const int g = find_genome(tile_off, n_genomes, tile, 0);
-    EmitToTable emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g, status};
+    EmitHash emit{table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), max_hash, flags + g, status};
     const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
     const uint32_t lut = 0x54474341u;
     for (int pos = threadIdx.x; pos < kTileBases; pos += blockDim.x) {
@@ -491,9 +472,10 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
         PANIB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st));
     }
 #endif
+    const HashConsts hc = make_hash_consts(seed, max_hash);
 #define PANIB_LAUNCH_K(KK)                                                                                   \
     sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, kK1DynSmem, st>>>( \
-        d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, seed, max_hash, d_nb, d_bmul,    \
+        d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, hc, d_nb, d_bmul,                \
         d_table, row_stride, d_flags, d_status, ticket)
     switch (k) {
     case 21: PANIB_LAUNCH_K(21); break;
