@@ -9,9 +9,10 @@ configuration: kernel K1 (hash + per-genome sort/dedup) over every genome, [all-
 sketches when N > 1], kernel K2 over every unordered genome pair, and the ANI kernel.
 
 * ``value``  whole-job genome pairs/s with the 2-bit packed genomes already resident in HBM.
-* ``e2e``    the same metric through the public engine API from HOST buffers: pinned ASCII genomes are
-             copied host->device, packed, sketched, intersected, and the two float64 ANI matrices are
-             copied back, all inside the timed region.
+* ``e2e``    the same metric through the public engine API from HOST buffers: the ASCII genomes are packed
+             (2 bits + validity bit per base) by the library's host threads into pinned memory, copied
+             host->device chunk by chunk while K1 hashes the chunks already there, intersected, and the two
+             float64 ANI matrices are copied back -- all inside the timed region.
 * ``roofline``       dominant kernel of the step, algorithmic bytes / CUDA-event time vs measured HBM peak.
 * ``cpu_baseline``   the oracle (CPU port of the same algorithm) timed on the host cores (rank 0).
 
@@ -314,8 +315,6 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     from pyani_plus_b200 import engine, multi_gpu
     from pyani_plus_b200 import stream as pstream
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     # stdout carries exactly ONE line (the JSON): whatever libraries print there while the job runs
@@ -323,8 +322,10 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from pyani_plus_b200 import run as run_mod
+
+    ctx = run_mod.DistContext.from_env()  # torchrun: one process per GPU, NCCL
+    world, rank = ctx.world, ctx.rank
     eng = engine.Engine(local_rank)
     dev = eng.device
 
@@ -340,12 +341,12 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     tile_off = np.zeros(per_rank + 1, dtype=np.int64)
     for i in range(per_rank):
         tile_off[i + 1] = tile_off[i] + (tiles_per if i < n_local else 1)
-    plan = eng.plan_stream(tile_off, scaled)
+    plan = run_mod.agree_row_stride(eng, tile_off, scaled, ctx)  # one row stride on every rank
     bufs = eng.alloc_stream_buffers(plan, ascii_too=False)
     tab = eng.alloc_table(plan)
     # e2e needs the whole ASCII stream in pinned host memory; skipped (null) for streams > 12 GB
     do_e2e = plan.n_bases <= (12 << 30) and not args.no_e2e
-    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True) if do_e2e else None
+    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8) if do_e2e else None  # what a FASTA reader hands over
     batch = 256  # genomes generated + packed per pass, so that the ASCII form is never fully resident
     for b0 in range(0, per_rank, batch):
         b1 = min(per_rank, b0 + batch)
@@ -363,33 +364,22 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             h_ascii[t0 * pstream.TILE: t1 * pstream.TILE].copy_(d_ascii)
         torch.cuda.synchronize()
         del d_ascii
-    if do_e2e:
-        bufs["ascii"] = torch.empty(plan.n_bases, dtype=torch.uint8, device=dev)
+    if do_e2e:  # pinned staging of the packed form: the host threads pack into it inside every e2e step
+        bufs["h_packed"] = torch.empty(plan.n_bases // 16, dtype=torch.int32, pin_memory=True)
+        bufs["h_mask"] = torch.empty(plan.n_bases // 32, dtype=torch.int32, pin_memory=True)
 
     n_rows = per_rank * world
-    size_hint = plan.sketch_size_hint()
-    if world > 1:  # all ranks must agree (genome lengths differ between slices in general)
-        hint_t = torch.tensor([size_hint], dtype=torch.int64, device=dev)
-        dist.all_reduce(hint_t, op=dist.ReduceOp.MAX)
-        size_hint = int(hint_t.item())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     result = {}
 
-    # several GPUs: finalize fused with the all-gather through peer-mapped memory when available
-    fused = None
-    if world > 1 and not args.nccl_gather:
-        fused = multi_gpu.SymmetricGather.create(per_rank, plan.row_stride, world, rank, dev)
-        ok = torch.tensor([1 if fused is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if not int(ok.item()):
-            fused = None
-
-    from pyani_plus_b200 import pipeline
-
-    stepper = pipeline.SourmashStep(eng, plan, bufs, tab, k, world=world, rank=rank, gather=fused,
-                                    size_hint=size_hint, h_ascii=h_ascii, k2_method=args.k2)
+    # the step is the package's (run.make_step): size hint agreed over the ranks; several GPUs: finalize fused
+    # with the all-gather through peer-mapped memory (an error if that cannot be set up, unless --nccl-gather)
+    stepper, exchange = run_mod.make_step(
+        eng, plan, bufs, tab, k, ctx, h_ascii=h_ascii, k2_method=args.k2, nccl_gather=args.nccl_gather,
+        host_threads=max(1, len(os.sched_getaffinity(0)) // max(1, world)))
+    size_hint = stepper.size_hint
     # the step as ONE CUDA graph launch (all ranks must agree, the gather has barriers inside)
     graphed: dict = {}
     per_step_launches: dict = {}
@@ -539,8 +529,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             e2e_t[key] = e2e_eager[key]
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        ctx.close()
+        if parity["ok"] is False:
+            sys.exit(3)
         return
 
     # ---- derived numbers
@@ -583,8 +574,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "warmup": args.warmup, "ms_per_step": dev_t["ms"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": config_dict(args.workload, world),
-        "exchange": (("finalize fused with the all-gather (peer-memory stores over NVLink)" if fused is not None
-                      else "NCCL all-gather of sketch rows") if world > 1 else None),
+        "exchange": exchange,
         "sketch_gbp_s": n * length / (dev_t["k1_ms"] * 1e-3) / 1e9,
         "pairs_per_s_k2": n_pairs / (dev_t["k2_ms"] * 1e-3),
         "stage_ms": {"k1_sketch": dev_t["k1_ms"], "allgather": dev_t["gather_ms"], "k2_intersect": dev_t["k2_ms"],
@@ -595,7 +585,11 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "cpu_baseline_detail": ({"sketch_gbp_s": cpu["sketch_gbp_s"],
                                  "pairs_per_s_intersect": cpu["pairs_per_s_intersect"]} if cpu else None),
         "e2e": ({"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_t["ms"],
-                 "h2d_bytes_per_step": int(plan.n_bases) * world,
+                 "h2d_bytes_per_step": int(plan.n_bases // 16 * 4 + plan.n_bases // 32 * 4) * world,
+                 "host_ascii_bytes_per_step": int(plan.n_bases) * world,
+                 "host_pack": {"threads_per_rank": min(stepper.host_threads, int(eng.lib.panib_host_threads())),
+                               "what": "ASCII -> 2-bit + validity mask on the host threads (AVX-512/AVX2), "
+                                       "inside the timed step, pipelined with the copies and K1"},
                  "d2h_bytes_per_step": int(2 * n_rows * n_rows * 8 + n_rows * 4) * world,
                  "stage_ms": {"h2d_pack_k1": e2e_t["k1_ms"], "allgather": e2e_t["gather_ms"],
                               "k2_intersect": e2e_t["k2_ms"]}} if e2e_t else
@@ -618,8 +612,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
     if parity["ok"] is False:
         print(f"PARITY FAILURE: result checksum {checksum} != oracle {expected}", file=sys.stderr, flush=True)
         sys.exit(3)

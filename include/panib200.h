@@ -72,6 +72,7 @@ extern "C" {
  * single all-gather of the rows carries the sizes along. */
 #define PANIB_ST_BUCKET_OVERFLOW 1 /* a sketch bucket filled up: re-run with more buckets           */
 #define PANIB_ST_SEGMENT_OVERFLOW 2/* a pairwise segment exceeded seg_cap: re-run with more cells    */
+#define PANIB_ST_INDEX_OVERFLOW 4  /* a rank's slice of the inverted index outgrew its table: re-run unsharded */
 
 /* ---- library ------------------------------------------------------------------------------ */
 PANIB_API const char *panib_version(void);                    /* "0.1.0 sm_100a ..."                        */
@@ -148,6 +149,31 @@ PANIB_API int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t 
                                       const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
                                       int64_t row_stride, int32_t *d_flags, int32_t *d_status, void *stream);
 
+/* ---- ingest (host): ASCII base stream -> packed 2-bit + validity mask on host threads ---------- */
+/* The host form of panib_pack_ascii (same packed words and mask bits), run on the library's pool of host
+ * threads (threads = 0: all the process may use; panib_host_threads() tells how many that is).  This is
+ * the reader side of the replacement for the reference's per-file hand-over of FASTA bytes to
+ * `sourmash scripts singlesketch` (pyani_plus/methods/sourmash.py:67-83; pyani_plus/utils.py:40-90):
+ * packing before the copy puts 0.375 instead of 1 byte per base on PCIe.  AVX-512 / AVX2 / scalar code
+ * chosen at run time; threads = -1 / -2 / -3 runs the scalar / AVX2 / AVX-512 form on the calling thread
+ * (tests).  n_bases must be a multiple of 32. */
+PANIB_API int panib_host_threads(void);
+PANIB_API int panib_pack_host(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
+                    int threads);
+
+/* Packed host-buffer form of panib_sketch_stream: the ingest pipeline.  h_packed / h_mask are (pinned) host
+ * buffers of n_bases/16 and n_bases/32 words.  With h_ascii != NULL the ASCII stream is packed into them by
+ * the host threads chunk by chunk, overlapped with the host->device copies of the packed chunks and with K1
+ * on the chunks already copied; with h_ascii == NULL they already hold the packed stream.  d_counts == NULL
+ * skips the finalize step (rows stay bucketed hash sets, as after panib_sketch_hash_only).  The call returns
+ * when all host work is done and all device work is enqueued on `stream`. */
+PANIB_API int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_packed, uint32_t *h_mask, int64_t n_bases,
+                             uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
+                             int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
+                             const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,
+                             int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
+                             int host_threads, void *stream);
+
 /* ---- stage 2 (kernel K2): all-vs-all sorted-sketch intersection -- replaces `manysearch` ---- */
 /* Queries are rows of (d_q_rows, d_q_counts, q_stride), subjects rows of (d_s_rows, ...); they may be
  * the same table.  symmetric != 0 requires the same table and computes only q < s, mirroring the
@@ -168,26 +194,33 @@ PANIB_API int64_t panib_intersect_fence_entries(int64_t nq, int64_t ns, uint64_t
 
 /* ---- stage 2, inverted-index form (csrc/index.cu): same counts as panib_intersect(symmetric=1), cost
  * proportional to what the genomes SHARE instead of N^2 x sketch size.  Replaces the same reference step
- * (pyani_plus/methods/sourmash.py:184-200).  All sketches are flattened to (hash, genome) entries
- * sorted by hash; hashes held by >= tau genomes become
- * columns of a bit matrix (AND+POPC over all genome pairs), rarer shared hashes are expanded pair by pair.
+ * (pyani_plus/methods/sourmash.py:184-200).  A sketch is a duplicate-free set, so the genomes holding a hash
+ * are found by a group-by over all (hash, genome) entries: a hand-written open-addressing hash table in
+ * global memory (atomicCAS on the key, atomicAdd for the entry's arrival index in its group; no sort, no
+ * library).  Hashes held by >= tau genomes become columns of a bit matrix (AND+POPC over all genome pairs),
+ * rarer shared hashes are expanded pair by pair from their member lists.
  * Entries: exact (d_offsets = int64[n+1] prefix sums of the sketch sizes, entries = their total) or padded
- * (d_offsets NULL, entries = n * cap, unused slots hold a key above max_hash: needs no host knowledge of the
- * sizes, so it can be captured in a CUDA graph; cap >= the largest sketch, a larger one raises
- * PANIB_ST_SEGMENT_OVERFLOW).  In the exact form cap only sizes the launch grid.
- * d_work: scratch of panib_index_workspace_bytes(n, entries, tau) bytes, d_stats: uint64[4] written by
- * panib_index_build = {bit-matrix columns, pairs expanded from rare hashes, distinct hashes (+1 if padded), 0}
- * so that the caller can compare the cost with the probing kernel before calling panib_index_count with the
- * SAME n / max_hash / entries / tau / d_work.  Requires entries < 2^31 and max_hash < 2^64 - 16 (scaled >= 2).
- * Offsets that do not match the sizes raise PANIB_ST_SEGMENT_OVERFLOW in d_status.
- * Multi-GPU: as panib_intersect (rank r computes the tiles / hashes it owns; the matrices sum). */
-PANIB_API int panib_index_workspace_bytes(int64_t n, int64_t entries, int tau, int64_t *bytes);
+ * (d_offsets NULL, entries = n * cap: needs no host knowledge of the sizes, so it can be captured in a CUDA
+ * graph; cap >= the largest sketch, a larger one raises PANIB_ST_SEGMENT_OVERFLOW).  In the exact form cap
+ * only sizes the launch grid.  d_work: scratch of panib_index_workspace_bytes(n, entries, tau, world) bytes,
+ * d_stats: uint64[4] written by panib_index_build = {bit-matrix columns, pairs expanded from rare hashes,
+ * distinct hashes, member-list words} of THIS rank, so that the caller can compare the cost with the probing
+ * kernel before calling panib_index_count with the SAME n / cap / entries / d_offsets / tau / rank / world /
+ * d_work.  Requires entries < 2^31 and max_hash < 2^64 - 16 (scaled >= 2).  Offsets that do not match the
+ * sizes raise PANIB_ST_SEGMENT_OVERFLOW in d_status.
+ * Multi-GPU: the HASH RANGE is sharded -- rank r of world indexes only the hashes in its 1/world slice of
+ * [0, max_hash], so every step shrinks with the number of ranks; the ranks' matrices sum to the result (as
+ * panib_intersect).  A slice holding more than twice its share of the entries raises
+ * PANIB_ST_INDEX_OVERFLOW (the caller then uses another form). */
+PANIB_API int panib_index_workspace_bytes(int64_t n, int64_t entries, int tau, int world, int64_t *bytes);
 PANIB_API int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts, int64_t stride, int64_t n,
                       uint64_t max_hash, int64_t cap, int64_t entries, const int64_t *d_offsets, int tau,
-                      void *d_work, int64_t work_bytes, uint64_t *d_stats, int32_t *d_status, void *stream);
-PANIB_API int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t entries, int tau,
-                      void *d_work, int64_t work_bytes, const uint64_t *d_stats, uint32_t *d_ov,
-                      int64_t ld_ov, int rank, int world, int32_t *d_status, void *stream);
+                      int rank, int world, void *d_work, int64_t work_bytes, uint64_t *d_stats,
+                      int32_t *d_status, void *stream);
+PANIB_API int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t cap, int64_t entries,
+                      const int64_t *d_offsets, int tau, void *d_work, int64_t work_bytes,
+                      const uint64_t *d_stats, uint32_t *d_ov, int64_t ld_ov, int rank, int world,
+                      int32_t *d_status, void *stream);
 
 /* ---- stage 3: containment -> ANI ------------------------------------------------------------ */
 /* identity[q,s] = max(ani(ov/|Q|), ani(ov/|S|)), cov_query[q,s] = ani(ov/|Q|),

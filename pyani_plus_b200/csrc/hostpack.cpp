@@ -13,6 +13,7 @@
 // the GPU tests check the host form against panib_pack_ascii.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -109,6 +110,10 @@ using PackFn = void (*)(const uint8_t *, int64_t, uint32_t *, uint32_t *);
 static PackFn choose_pack(int force) {
     // force: 0 = best available, 1 = scalar, 2 = AVX2, 3 = AVX-512 (tests); unavailable -> nullptr
     __builtin_cpu_init();
+    if (force == 0) {  // PANIB_PACK_ISA=scalar|avx2|avx512 pins the pool's code path (diagnostics)
+        const char *e = getenv("PANIB_PACK_ISA");
+        if (e) force = !strcmp(e, "scalar") ? 1 : !strcmp(e, "avx2") ? 2 : !strcmp(e, "avx512") ? 3 : 0;
+    }
     const bool has512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
     const bool has2 = __builtin_cpu_supports("avx2");
     switch (force) {

@@ -1,28 +1,36 @@
 // index.cu -- kernel K2, inverted-index form ("which genomes hold this hash?").
 //
 // The probing kernel in pairwise.cu touches every element of both sketches for every pair: its cost is
-// N^2 * |sketch| whatever the genomes share.  This form costs what the genomes SHARE.  All sketches are
-// flattened to (hash, genome) entries and sorted by hash (CUB radix sort); a run of equal hashes is the
-// list of genomes holding that hash, and it contributes +1 to ov[i][j] for every pair of its members:
+// N^2 * |sketch| whatever the genomes share.  This form costs what the genomes SHARE.  A sketch is a
+// duplicate-free set, so "how many genomes hold hash h" is a group-by over all (hash, genome) entries, and
+// every group of m genomes adds +1 to ov[i][j] for each of its m(m-1)/2 pairs.  The group-by is a hash table
+// in global memory, hand-written (no sort, no library call):
 //
-//   * frequent hashes (run length >= tau) become columns of a genome x column BIT MATRIX, and
-//     ov[i][j] += popcount(row_i AND row_j) is computed for all pairs by a tiled AND+POPC kernel
-//     (64 x 64 genome tiles, 4 x 4 pairs per thread, 32-word chunks staged in shared memory);
-//   * rare hashes (2 <= run length < tau) are expanded pair by pair with atomicAdd into ov
-//     (at most tau - 1 adds per entry);
-//   * hashes held by one genome contribute nothing and are dropped.
+//   1. insert   every entry looks its hash up in an open-addressing table (atomicCAS on the key) and takes a
+//               ticket from the slot's counter (atomicAdd): it now knows its group (slot) and its arrival
+//               index in the group.  Sketch hashes are uniform, so the slot is an ORDER-PRESERVING function
+//               of the hash, and the grid walks "same chunk of every genome" before the next chunk: blocks in
+//               flight touch one window of the table, which stays in L2.
+//   2. classify the first arrival of each group reads the final count m: m >= tau -> the hash becomes a column
+//               of a genome x column BIT MATRIX; 2 <= m < tau -> it gets room for its member list; m == 1
+//               contributes nothing.  Columns and list space come from warp-aggregated atomic counters.
+//   3. emit     every entry sets its bit (frequent) or writes its genome into its group's list (rare);
+//   4. count    rare groups are expanded pair by pair with atomicAdd into ov (<= tau - 1 adds per entry);
+//               frequent hashes: ov[i][j] += popcount(row_i AND row_j) for all pairs by a tiled AND+POPC
+//               kernel (64 x 64 genome tiles, 4 x 4 pairs per thread, 32-word chunks in shared memory);
+//   5. mirror   lower triangle := upper, diagonal := sketch sizes.
 //
-// The entries are either exact (offsets = prefix sums of the sketch sizes, computed by the caller) or
-// padded to `cap` slots per genome with a key above max_hash (no host knowledge of the sizes needed:
-// the form a captured CUDA graph uses).
+// Multi-GPU: the HASH RANGE is sharded -- rank r inserts only the entries whose hash falls into its 1/world
+// slice of [0, max_hash], so table, lists, bit-matrix columns and pair expansion all shrink with the number
+// of ranks; every rank runs all genome tiles over its own columns and the ranks' matrices sum to the result.
 //
-// Results are identical to the probing kernel (exact integer counts); which form is cheaper depends
-// on the data, so the host chooses (engine.py: Engine.intersect(method="auto")) from the statistics
-// panib_index_build returns.  Replaces the same reference step as pairwise.cu: the external
+// Entries are indexed exactly (offsets = prefix sums of the sketch sizes, computed by the caller) or padded
+// (`cap` slots per genome: no host knowledge of the sizes, the form a captured CUDA graph uses).
+//
+// Results are identical to the probing kernel (exact integer counts; additions commute); which form is
+// cheaper depends on the data, so the host chooses (engine.py: Engine.intersect(method="auto")) from the
+// statistics panib_index_build returns.  Replaces the same reference step as pairwise.cu: the external
 // `sourmash scripts manysearch` call in pyani_plus/methods/sourmash.py:184-200.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include "common.cuh"
 
 namespace panib {
@@ -30,120 +38,173 @@ namespace panib {
 constexpr int kIdxThreads = 256;
 constexpr int kDenseTile = 64;    // genomes per tile side of the AND+POPC kernel
 constexpr int kDenseChunk = 32;   // bit-matrix words staged per step
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+constexpr uint32_t kFrequent = 0x80000000u;  // taux flag: the low bits are a bit-matrix column
 
-// entry e = g * cap + i: hash i of genome g, or the pad key (> max_hash) beyond the genome's size
-__global__ void __launch_bounds__(kIdxThreads)
-index_flatten_kernel(const uint64_t *__restrict__ rows, const int32_t *__restrict__ counts, int64_t stride, int n,
-                     int cap, uint64_t pad_key, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                     int32_t *status) {
-    const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    if (e >= (int64_t)n * cap) return;
-    const int g = (int)(e / cap), i = (int)(e - (int64_t)g * cap);
-    const int c = counts[g];
-    if (i == 0 && c > cap && status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);  // cap too small: re-plan
-    keys[e] = i < c ? rows[(size_t)g * stride + i] : pad_key;
-    vals[e] = (uint32_t)g;
+struct IndexShard {
+    uint64_t wmul;   // owner(h) = min(world-1, mulhi(h, wmul))
+    uint64_t smul;   // slot(h)  = mulhi(h, smul) & mask: order-preserving inside a rank's hash range
+    uint32_t mask;   // table slots - 1
+    int rank, world;
+};
+
+__device__ __forceinline__ int64_t entry_index(int g, int i, int cap, const int64_t *__restrict__ offsets) {
+    return offsets ? offsets[g] + i : (int64_t)g * cap + i;
 }
 
-// exact-size form: genome g's hashes go to entries offsets[g] .. offsets[g] + counts[g] (no pad entries);
-// grid = (chunks of the largest sketch, genomes)
+// step 1.  grid = (genomes, chunks of 256 sketch positions): x (fast) walks the genomes of one chunk.
 __global__ void __launch_bounds__(kIdxThreads)
-index_flatten_exact_kernel(const uint64_t *__restrict__ rows, const int32_t *__restrict__ counts, int64_t stride,
-                           int n, int cap, const int64_t *__restrict__ offsets, int64_t total,
-                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int32_t *status) {
-    // `cap` only sizes the grid: a genome larger than the hint is still flattened completely (strided loop)
-    (void)cap;
-    for (int g = blockIdx.y; g < n; g += gridDim.y) {
+index_insert_kernel(const uint64_t *__restrict__ rows, const int32_t *__restrict__ counts, int64_t stride, int n,
+                    int cap, const int64_t *__restrict__ offsets, int64_t total, uint64_t max_hash, IndexShard sh,
+                    unsigned long long *__restrict__ tkeys, uint32_t *__restrict__ tcount,
+                    uint32_t *__restrict__ eslot, uint32_t *__restrict__ eidx, int32_t *status) {
+    for (int g = blockIdx.x; g < n; g += gridDim.x) {
         const int c = counts[g];
-        const int64_t at = offsets[g];
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (at < 0 || at + c > total) && status)
-            atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);  // offsets do not match the sizes
-        for (int i = blockIdx.x * kIdxThreads + threadIdx.x; i < c; i += gridDim.x * kIdxThreads) {
-            if (at + i < total) {
-                keys[at + i] = rows[(size_t)g * stride + i];
-                vals[at + i] = (uint32_t)g;
+        if (blockIdx.y == 0 && threadIdx.x == 0 && status) {
+            const int64_t at = entry_index(g, 0, cap, offsets);
+            if ((!offsets && c > cap) || at < 0 || at + (offsets ? c : 0) > total)
+                atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);  // cap too small / offsets do not match the sizes
+        }
+        for (int i = blockIdx.y * kIdxThreads + threadIdx.x; i < c; i += gridDim.y * kIdxThreads) {
+            if (!offsets && i >= cap) break;
+            const int64_t e = entry_index(g, i, cap, offsets);
+            if (e < 0 || e >= total) continue;
+            const uint64_t h = rows[(size_t)g * stride + i];
+            uint32_t slot = kNoSlot, arrival = 0;
+            int owner = 0;
+            if (sh.world > 1) {
+                owner = (int)__umul64hi(h, sh.wmul);
+                if (owner >= sh.world) owner = sh.world - 1;
+            }
+            if (h <= max_hash && owner == sh.rank) {
+                uint32_t s = (uint32_t)__umul64hi(h, sh.smul) & sh.mask;
+                for (uint32_t probe = 0; probe <= sh.mask; probe++) {
+                    const unsigned long long prev = atomicCAS(&tkeys[s], (unsigned long long)kEmpty, (unsigned long long)h);
+                    if (prev == kEmpty || prev == h) { slot = s; break; }
+                    s = (s + 1) & sh.mask;
+                }
+                if (slot == kNoSlot) { if (status) atomicOr(status, PANIB_ST_INDEX_OVERFLOW); }
+                else arrival = atomicAdd(&tcount[slot], 1u);
+            }
+            eslot[e] = slot;
+            eidx[e] = arrival;
+        }
+    }
+}
+
+// step 2: one thread per entry; the group's first arrival classifies the group.
+// stats: [0] columns, [1] pairs the rare groups expand to, [2] distinct hashes, [3] list words handed out
+__global__ void __launch_bounds__(kIdxThreads)
+index_classify_kernel(const int32_t *__restrict__ counts, int n, int cap, const int64_t *__restrict__ offsets,
+                      int64_t total, int tau, const uint32_t *__restrict__ tcount, uint32_t *__restrict__ taux,
+                      const uint32_t *__restrict__ eslot, const uint32_t *__restrict__ eidx,
+                      unsigned long long *__restrict__ stats) {
+    const unsigned lane = threadIdx.x & 31;
+    for (int g = blockIdx.x; g < n; g += gridDim.x) {
+        const int c = offsets ? counts[g] : min(counts[g], cap);
+        const int rounds = (c + (int)(gridDim.y * kIdxThreads) - 1) / (int)(gridDim.y * kIdxThreads);
+        for (int r = 0; r < rounds; r++) {  // whole warps stay in the loop: the ballots below need them
+            const int i = (r * gridDim.y + blockIdx.y) * kIdxThreads + threadIdx.x;
+            uint32_t slot = kNoSlot, m = 0;
+            if (i < c) {
+                const int64_t e = entry_index(g, i, cap, offsets);
+                if (e >= 0 && e < total && eidx[e] == 0) slot = eslot[e];
+                if (slot != kNoSlot) m = tcount[slot];
+            }
+            const bool frequent = m >= (uint32_t)tau, rare = m >= 2 && !frequent;
+            // columns: one atomic per warp
+            const unsigned fmask = __ballot_sync(0xFFFFFFFFu, frequent);
+            unsigned long long cbase = 0;
+            if (fmask) {
+                if (lane == (unsigned)(__ffs(fmask) - 1)) cbase = atomicAdd(stats + 0, (unsigned long long)__popc(fmask));
+                cbase = __shfl_sync(0xFFFFFFFFu, cbase, __ffs(fmask) - 1);
+            }
+            // list space: warp-wide exclusive scan of the rare group sizes, one atomic per warp
+            uint32_t incl = rare ? m : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (unsigned)o) incl += v;
+            }
+            const uint32_t wsum = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            unsigned long long lbase = 0;
+            if (wsum) {
+                if (lane == 31) lbase = atomicAdd(stats + 3, (unsigned long long)wsum);
+                lbase = __shfl_sync(0xFFFFFFFFu, lbase, 31);
+            }
+            if (frequent) taux[slot] = kFrequent | (uint32_t)(cbase + __popc(fmask & ((1u << lane) - 1u)));
+            else if (rare) taux[slot] = (uint32_t)(lbase + incl - m);
+            unsigned long long pairs = rare ? (unsigned long long)m * (m - 1) / 2ull : 0ull;
+            unsigned long long distinct = slot != kNoSlot ? 1ull : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+                distinct += __shfl_xor_sync(0xFFFFFFFFu, distinct, o);
+            }
+            if (lane == 0) {
+                if (pairs) atomicAdd(stats + 1, pairs);
+                if (distinct) atomicAdd(stats + 2, distinct);
             }
         }
     }
 }
 
+// step 3: bits of the frequent hashes, member lists of the rare ones
 __global__ void __launch_bounds__(kIdxThreads)
-index_heads_kernel(const uint64_t *__restrict__ keys, int64_t total, int32_t *__restrict__ head) {
-    const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    if (e >= total) return;
-    head[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1 : 0;
-}
-
-// gidx = inclusive scan of the head flags: entry e belongs to run gidx[e] - 1; start[r] = first entry of run r
-__global__ void __launch_bounds__(kIdxThreads)
-index_starts_kernel(const int32_t *__restrict__ gidx, int64_t total, int32_t *__restrict__ start,
-                    unsigned long long *__restrict__ stats) {
-    const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    if (e >= total) return;
-    const int r = gidx[e];
-    if (e == 0 || gidx[e - 1] != r) start[r - 1] = (int32_t)e;
-    if (e == total - 1) {
-        start[r] = (int32_t)total;
-        stats[2] = (unsigned long long)r;  // number of runs (the pad run included)
-    }
-}
-
-// per run: frequent -> a bit-matrix column, rare -> pair expansion, single / pad -> nothing
-__global__ void __launch_bounds__(kIdxThreads)
-index_classify_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ start,
-                      const int32_t *__restrict__ gidx, int64_t total, uint64_t max_hash, int tau,
-                      int32_t *__restrict__ densecol, unsigned long long *__restrict__ stats) {
-    const int64_t r = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    const bool live = r < gidx[total - 1];
-    unsigned long long pairs = 0ull;
-    if (live) {
-        const int s = start[r], m = start[r + 1] - s;
-        int col = -1;
-        if (keys[s] <= max_hash) {
-            if (m >= tau) col = (int)atomicAdd(stats + 0, 1ull);
-            else if (m >= 2) pairs = (unsigned long long)m * (unsigned long long)(m - 1) / 2ull;
+index_emit_kernel(const int32_t *__restrict__ counts, int n, int cap, const int64_t *__restrict__ offsets,
+                  int64_t total, int tau, const uint32_t *__restrict__ tcount, const uint32_t *__restrict__ taux,
+                  const uint32_t *__restrict__ eslot, const uint32_t *__restrict__ eidx,
+                  uint32_t *__restrict__ lists, int64_t list_cap, uint32_t *__restrict__ bits, int64_t wcap,
+                  int32_t *status) {
+    for (int g = blockIdx.x; g < n; g += gridDim.x) {
+        const int c = offsets ? counts[g] : min(counts[g], cap);
+        for (int i = blockIdx.y * kIdxThreads + threadIdx.x; i < c; i += gridDim.y * kIdxThreads) {
+            const int64_t e = entry_index(g, i, cap, offsets);
+            if (e < 0 || e >= total) continue;
+            const uint32_t slot = eslot[e];
+            if (slot == kNoSlot) continue;
+            const uint32_t m = tcount[slot];
+            if (m < 2) continue;
+            const uint32_t aux = taux[slot];
+            if (m >= (uint32_t)tau) {
+                const uint32_t col = aux & ~kFrequent;
+                if ((int64_t)(col >> 5) >= wcap) { if (status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW); continue; }
+                atomicOr(bits + (size_t)g * wcap + (col >> 5), 1u << (col & 31));
+            } else {
+                const int64_t at = (int64_t)aux + eidx[e];
+                if (at < list_cap) lists[at] = (uint32_t)g;
+                else if (status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);
+            }
         }
-        densecol[r] = col;
     }
-    // one atomic per warp for the rare-pair total (millions of runs would otherwise queue on one address)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
-    if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(stats + 1, pairs);
 }
 
+// step 4a: rare hashes -- every entry pairs with the LATER arrivals of its group, so each unordered pair is
+// written once; (min, max) puts it in the upper triangle whatever the arrival order was
 __global__ void __launch_bounds__(kIdxThreads)
-index_bits_kernel(const uint32_t *__restrict__ vals, const int32_t *__restrict__ gidx,
-                  const int32_t *__restrict__ densecol, int64_t total, int n, uint32_t *__restrict__ bits,
-                  int64_t wcap, int32_t *status) {
-    const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    if (e >= total) return;
-    const int col = densecol[gidx[e] - 1];
-    if (col < 0) return;
-    if ((col >> 5) >= wcap || vals[e] >= (uint32_t)n) {  // cannot happen with a consistent index
-        if (status) atomicOr(status, PANIB_ST_SEGMENT_OVERFLOW);
-        return;
-    }
-    atomicOr(bits + (size_t)vals[e] * wcap + (col >> 5), 1u << (col & 31));
-}
-
-// rare hashes: entry e pairs with the later members of its run (genome ids ascend inside a run because
-// the radix sort is stable and the flattening is genome-major), so only i < j is written
-__global__ void __launch_bounds__(kIdxThreads)
-index_sparse_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                    const int32_t *__restrict__ gidx, const int32_t *__restrict__ start,
-                    const int32_t *__restrict__ densecol, int64_t total, int n, uint64_t max_hash,
-                    uint32_t *__restrict__ ov, int64_t ld, int rank, int world) {
-    const int64_t e = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
-    if (e >= total) return;
-    const int r = gidx[e] - 1;
-    if (densecol[r] >= 0 || keys[e] > max_hash) return;
-    if (world > 1 && r % world != rank) return;
-    const int end = start[r + 1];
-    const uint32_t i = vals[e];
-    if (i >= (uint32_t)n) return;
-    for (int64_t x = e + 1; x < end && x < total; x++) {
-        const uint32_t j = vals[x];
-        if (j < (uint32_t)n) atomicAdd(ov + (size_t)i * ld + j, 1u);
+index_sparse_kernel(const int32_t *__restrict__ counts, int n, int cap, const int64_t *__restrict__ offsets,
+                    int64_t total, int tau, const uint32_t *__restrict__ tcount, const uint32_t *__restrict__ taux,
+                    const uint32_t *__restrict__ eslot, const uint32_t *__restrict__ eidx,
+                    const uint32_t *__restrict__ lists, int64_t list_cap, uint32_t *__restrict__ ov, int64_t ld) {
+    for (int g = blockIdx.x; g < n; g += gridDim.x) {
+        const int c = offsets ? counts[g] : min(counts[g], cap);
+        for (int i = blockIdx.y * kIdxThreads + threadIdx.x; i < c; i += gridDim.y * kIdxThreads) {
+            const int64_t e = entry_index(g, i, cap, offsets);
+            if (e < 0 || e >= total) continue;
+            const uint32_t slot = eslot[e];
+            if (slot == kNoSlot) continue;
+            const uint32_t m = tcount[slot];
+            if (m < 2 || m >= (uint32_t)tau) continue;
+            const int64_t base = (int64_t)taux[slot];
+            for (uint32_t b = eidx[e] + 1; b < m; b++) {
+                if (base + b >= list_cap) break;
+                const uint32_t other = lists[base + b];
+                if (other >= (uint32_t)n || other == (uint32_t)g) continue;
+                const uint32_t lo = other < (uint32_t)g ? other : (uint32_t)g;
+                const uint32_t hi = other < (uint32_t)g ? (uint32_t)g : other;
+                atomicAdd(ov + (size_t)lo * ld + hi, 1u);
+            }
+        }
     }
 }
 
@@ -154,7 +215,7 @@ index_dense_kernel(const uint32_t *__restrict__ bits, int64_t wcap, const unsign
                    int n, uint32_t *__restrict__ ov, int64_t ld, int rank, int world) {
     const int I = blockIdx.y, J = blockIdx.x;
     if (I > J) return;
-    if (world > 1 && (int)(((int64_t)I * gridDim.x + J) % world) != rank) return;
+    (void)rank; (void)world;  // hash-range sharding: every rank runs all tiles over its OWN columns
     int64_t W = (int64_t)((stats[0] + 31ull) >> 5);
     if (W > wcap) W = wcap;
     __shared__ uint32_t sa[kDenseChunk][kDenseTile + 1];
@@ -223,62 +284,70 @@ index_mirror_kernel(uint32_t *__restrict__ ov, int64_t ld, int n, const int32_t 
 }
 
 struct IndexLayout {
-    int64_t total, wcap;
-    size_t off_keys[2], off_vals[2], off_bits, off_temp, temp_bytes, bytes;
+    int64_t total, wcap, slots;
+    size_t off_keys, off_count, off_aux, off_eslot, off_eidx, off_lists, off_bits, bytes;
 };
 
-static int index_layout(int64_t n, int64_t total, int tau, IndexLayout *L) {
-    if (n <= 0 || total <= 0 || tau < 2 || total >= 0x7FFFFF00LL) {
-        set_error("panib_index: n=%lld entries=%lld tau=%d out of range (entries must be < 2^31)", (long long)n,
-                  (long long)total, tau);
+static int index_layout(int64_t n, int64_t total, int tau, int world, IndexLayout *L) {
+    if (n <= 0 || total <= 0 || tau < 2 || total >= 0x7FFFFF00LL || world < 1) {
+        set_error("panib_index: n=%lld entries=%lld tau=%d world=%d out of range (entries must be < 2^31)",
+                  (long long)n, (long long)total, tau, world);
         return PANIB_E_ARG;
     }
     L->total = total;
     L->wcap = (L->total / tau + 31) / 32 + 1;
-    size_t sort_bytes = 0, scan_bytes = 0;
-    if (cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)L->total, 0,
-                                        64) != cudaSuccess ||
-        cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
-                                      (int)L->total) != cudaSuccess) {
-        set_error("panib_index: CUB temporary-storage query failed");
-        return PANIB_E_CUDA;
-    }
+    // table: twice the entries a rank can own; a rank owns 1/world of the hash range, sized for twice its share
+    int64_t own = world == 1 ? total : 2 * (total / world) + 4096;
+    if (own > total) own = total;
+    int64_t slots = 1024;
+    while (slots < 2 * own) slots <<= 1;
+    L->slots = slots;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t at = 0;
-    for (int b = 0; b < 2; b++) { L->off_keys[b] = at; at = align(at + (size_t)(L->total + 2) * 8); }
-    for (int b = 0; b < 2; b++) { L->off_vals[b] = at; at = align(at + (size_t)(L->total + 2) * 4); }
-    L->off_bits = at; at = align(at + (size_t)n * L->wcap * 4);
-    L->temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
-    L->off_temp = at; at = align(at + L->temp_bytes);
+    L->off_keys = at;  at = align(at + (size_t)slots * 8);
+    L->off_count = at; at = align(at + (size_t)slots * 4);
+    L->off_aux = at;   at = align(at + (size_t)slots * 4);
+    L->off_eslot = at; at = align(at + (size_t)total * 4);
+    L->off_eidx = at;  at = align(at + (size_t)total * 4);
+    L->off_lists = at; at = align(at + (size_t)total * 4);
+    L->off_bits = at;  at = align(at + (size_t)n * L->wcap * 4);
     L->bytes = at;
     return PANIB_OK;
+}
+
+static dim3 entry_grid(int64_t n, int64_t cap) {  // x = genomes (fast), y = chunks of the longest sketch
+    int64_t gy = (cap + kIdxThreads - 1) / kIdxThreads;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    const int64_t gx = n < (1 << 30) ? n : (1 << 30);
+    return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
 }  // namespace panib
 
 using namespace panib;
 
-extern "C" int panib_index_workspace_bytes(int64_t n, int64_t total, int tau, int64_t *bytes) {
+extern "C" int panib_index_workspace_bytes(int64_t n, int64_t total, int tau, int world, int64_t *bytes) {
     IndexLayout L;
-    int rc = index_layout(n, total, tau, &L);
+    int rc = index_layout(n, total, tau, world, &L);
     if (rc) return rc;
     *bytes = (int64_t)L.bytes;
     return PANIB_OK;
 }
 
-// Phase 1: flatten, sort, find the runs, classify them.  d_stats (uint64[4]) receives
-// [0] frequent hashes (bit-matrix columns), [1] pairs the rare hashes expand to, [2] runs, [3] unused.
+// Phase 1: insert every entry this rank owns, classify the groups.  d_stats (uint64[4]) receives
+// [0] frequent hashes (bit-matrix columns), [1] pairs the rare hashes expand to, [2] distinct hashes,
+// [3] list words -- all for THIS rank's slice of the hash range.
 extern "C" int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts, int64_t stride, int64_t n,
                                  uint64_t max_hash, int64_t cap, int64_t total, const int64_t *d_offsets, int tau,
-                                 void *d_work, int64_t work_bytes, uint64_t *d_stats, int32_t *d_status,
-                                 void *stream) {
+                                 int rank, int world, void *d_work, int64_t work_bytes, uint64_t *d_stats,
+                                 int32_t *d_status, void *stream) {
     IndexLayout L;
-    int rc = index_layout(n, total, tau, &L);
+    int rc = index_layout(n, total, tau, world, &L);
     if (rc) return rc;
-    if (cap <= 0 || cap > 0x7FFFFFFFLL || (!d_offsets && total != n * cap)) {
-        set_error("panib_index_build: cap=%lld / entries=%lld inconsistent (padded form needs entries == n*cap)",
-                  (long long)cap, (long long)total);
+    if (cap <= 0 || cap > 0x7FFFFFFFLL || (!d_offsets && total != n * cap) || rank < 0 || rank >= world) {
+        set_error("panib_index_build: cap=%lld / entries=%lld / rank %d of %d inconsistent (padded form needs "
+                  "entries == n*cap)", (long long)cap, (long long)total, rank, world);
         return PANIB_E_ARG;
     }
     if (!d_work || work_bytes < (int64_t)L.bytes || !d_stats || max_hash >= 0xFFFFFFFFFFFFFFF0ull) {
@@ -288,84 +357,73 @@ extern "C" int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts
     }
     cudaStream_t st = (cudaStream_t)stream;
     char *base = static_cast<char *>(d_work);
-    uint64_t *keys[2] = {reinterpret_cast<uint64_t *>(base + L.off_keys[0]),
-                         reinterpret_cast<uint64_t *>(base + L.off_keys[1])};
-    uint32_t *vals[2] = {reinterpret_cast<uint32_t *>(base + L.off_vals[0]),
-                         reinterpret_cast<uint32_t *>(base + L.off_vals[1])};
-    const int64_t T = L.total;
-    const unsigned blocks = (unsigned)((T + kIdxThreads - 1) / kIdxThreads);
-    const uint64_t pad_key = max_hash + 1;
-    int end_bit = 1;
-    while (end_bit < 64 && (pad_key >> end_bit)) end_bit++;
+    auto *tkeys = reinterpret_cast<unsigned long long *>(base + L.off_keys);
+    auto *tcount = reinterpret_cast<uint32_t *>(base + L.off_count);
+    auto *taux = reinterpret_cast<uint32_t *>(base + L.off_aux);
+    auto *eslot = reinterpret_cast<uint32_t *>(base + L.off_eslot);
+    auto *eidx = reinterpret_cast<uint32_t *>(base + L.off_eidx);
+    // order-preserving maps of the hash range [0, max_hash]: onto the ranks, and onto world * slots table
+    // positions (a rank's slice then covers its own table once)
+    const unsigned __int128 range = (unsigned __int128)max_hash + 1;
+    auto scale = [&](unsigned __int128 parts) -> uint64_t {
+        const unsigned __int128 m = (parts << 64) / range;
+        return m > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)m;
+    };
+    IndexShard sh;
+    sh.wmul = scale((unsigned __int128)world);
+    sh.smul = scale((unsigned __int128)world * (unsigned __int128)L.slots);
+    sh.mask = (uint32_t)(L.slots - 1);
+    sh.rank = rank;
+    sh.world = world;
 
     PANIB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(uint64_t), st));
-    if (d_offsets) {
-        const dim3 grid((unsigned)((cap + kIdxThreads - 1) / kIdxThreads), (unsigned)(n < 65535 ? n : 65535));
-        index_flatten_exact_kernel<<<grid, kIdxThreads, 0, st>>>(d_rows, d_counts, stride, (int)n, (int)cap, d_offsets,
-                                                                 T, keys[0], vals[0], d_status);
-    } else {
-        index_flatten_kernel<<<blocks, kIdxThreads, 0, st>>>(d_rows, d_counts, stride, (int)n, (int)cap, pad_key,
-                                                             keys[0], vals[0], d_status);
-    }
-    rc = check_launch("index_flatten_kernel");
+    PANIB_CUDA(cudaMemsetAsync(tkeys, 0xFF, (size_t)L.slots * 8, st));
+    PANIB_CUDA(cudaMemsetAsync(tcount, 0, (size_t)L.slots * 4, st));
+    const dim3 grid = entry_grid(n, cap);
+    index_insert_kernel<<<grid, kIdxThreads, 0, st>>>(d_rows, d_counts, stride, (int)n, (int)cap, d_offsets, L.total,
+                                                      max_hash, sh, tkeys, tcount, eslot, eidx, d_status);
+    rc = check_launch("index_insert_kernel");
     if (rc) return rc;
-    // keys[0]/vals[0] = flattened input, keys[1]/vals[1] = sorted output; after the sort the input
-    // buffers are re-used: vals[0] -> head flags, then densecol; keys[0] -> gidx (T+1 ints) + start (T+1 ints)
-    size_t temp = L.temp_bytes;
-    PANIB_CUDA(cub::DeviceRadixSort::SortPairs(base + L.off_temp, temp, keys[0], keys[1], vals[0], vals[1], (int)T,
-                                               0, end_bit, st));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    const uint64_t *skeys = keys[1];
-    int32_t *head = reinterpret_cast<int32_t *>(vals[0]);
-    int32_t *gidx = reinterpret_cast<int32_t *>(keys[0]);
-    int32_t *start = gidx + (T + 1);
-    index_heads_kernel<<<blocks, kIdxThreads, 0, st>>>(skeys, T, head);
-    rc = check_launch("index_heads_kernel");
-    if (rc) return rc;
-    temp = L.temp_bytes;
-    PANIB_CUDA(cub::DeviceScan::InclusiveSum(base + L.off_temp, temp, head, gidx, (int)T, st));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    index_starts_kernel<<<blocks, kIdxThreads, 0, st>>>(gidx, T, start,
+    index_classify_kernel<<<grid, kIdxThreads, 0, st>>>(d_counts, (int)n, (int)cap, d_offsets, L.total, tau, tcount,
+                                                        taux, eslot, eidx,
                                                         reinterpret_cast<unsigned long long *>(d_stats));
-    rc = check_launch("index_starts_kernel");
-    if (rc) return rc;
-    index_classify_kernel<<<blocks, kIdxThreads, 0, st>>>(skeys, start, gidx, T, max_hash, tau, head,
-                                                          reinterpret_cast<unsigned long long *>(d_stats));
     return check_launch("index_classify_kernel");
 }
 
 // Phase 2: intersection sizes from the index built by panib_index_build with the SAME arguments.
 // d_ov (uint32 [n x ld_ov]) is fully overwritten: counts for i != j (mirrored), sketch sizes on the
 // diagonal (rank 0 only, as panib_intersect); the ranks' matrices sum to the full result.
-extern "C" int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t total, int tau,
-                                 void *d_work, int64_t work_bytes, const uint64_t *d_stats, uint32_t *d_ov,
-                                 int64_t ld_ov, int rank, int world, int32_t *d_status, void *stream) {
+extern "C" int panib_index_count(const int32_t *d_counts, int64_t n, uint64_t max_hash, int64_t cap, int64_t total,
+                                 const int64_t *d_offsets, int tau, void *d_work, int64_t work_bytes,
+                                 const uint64_t *d_stats, uint32_t *d_ov, int64_t ld_ov, int rank, int world,
+                                 int32_t *d_status, void *stream) {
+    (void)max_hash;
     IndexLayout L;
-    int rc = index_layout(n, total, tau, &L);
+    int rc = index_layout(n, total, tau, world, &L);
     if (rc) return rc;
-    if (!d_work || work_bytes < (int64_t)L.bytes || ld_ov < n || world < 1 || rank < 0 || rank >= world) {
+    if (!d_work || work_bytes < (int64_t)L.bytes || ld_ov < n || rank < 0 || rank >= world || cap <= 0) {
         set_error("panib_index_count: bad workspace / ld_ov / rank arguments");
         return PANIB_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
     char *base = static_cast<char *>(d_work);
-    const int64_t T = L.total;
-    const unsigned blocks = (unsigned)((T + kIdxThreads - 1) / kIdxThreads);
-    const uint64_t *skeys = reinterpret_cast<const uint64_t *>(base + L.off_keys[1]);
-    const uint32_t *svals = reinterpret_cast<const uint32_t *>(base + L.off_vals[1]);
-    const int32_t *densecol = reinterpret_cast<const int32_t *>(base + L.off_vals[0]);
-    const int32_t *gidx = reinterpret_cast<const int32_t *>(base + L.off_keys[0]);
-    const int32_t *start = gidx + (T + 1);
+    const auto *tcount = reinterpret_cast<const uint32_t *>(base + L.off_count);
+    const auto *taux = reinterpret_cast<const uint32_t *>(base + L.off_aux);
+    const auto *eslot = reinterpret_cast<const uint32_t *>(base + L.off_eslot);
+    const auto *eidx = reinterpret_cast<const uint32_t *>(base + L.off_eidx);
+    auto *lists = reinterpret_cast<uint32_t *>(base + L.off_lists);
     uint32_t *bits = reinterpret_cast<uint32_t *>(base + L.off_bits);
     const unsigned long long *stats = reinterpret_cast<const unsigned long long *>(d_stats);
 
     PANIB_CUDA(cudaMemsetAsync(d_ov, 0, (size_t)n * ld_ov * sizeof(uint32_t), st));
     PANIB_CUDA(cudaMemsetAsync(bits, 0, (size_t)n * L.wcap * sizeof(uint32_t), st));
-    index_bits_kernel<<<blocks, kIdxThreads, 0, st>>>(svals, gidx, densecol, T, (int)n, bits, L.wcap, d_status);
-    rc = check_launch("index_bits_kernel");
+    const dim3 grid = entry_grid(n, cap);
+    index_emit_kernel<<<grid, kIdxThreads, 0, st>>>(d_counts, (int)n, (int)cap, d_offsets, L.total, tau, tcount, taux,
+                                                    eslot, eidx, lists, L.total, bits, L.wcap, d_status);
+    rc = check_launch("index_emit_kernel");
     if (rc) return rc;
-    index_sparse_kernel<<<blocks, kIdxThreads, 0, st>>>(skeys, svals, gidx, start, densecol, T, (int)n, max_hash, d_ov,
-                                                        ld_ov, rank, world);
+    index_sparse_kernel<<<grid, kIdxThreads, 0, st>>>(d_counts, (int)n, (int)cap, d_offsets, L.total, tau, tcount,
+                                                      taux, eslot, eidx, lists, L.total, d_ov, ld_ov);
     rc = check_launch("index_sparse_kernel");
     if (rc) return rc;
     const unsigned nt = (unsigned)((n + kDenseTile - 1) / kDenseTile);

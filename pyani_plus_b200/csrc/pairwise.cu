@@ -16,6 +16,11 @@
 // resident: HBM traffic is far below the algorithmic 8(|A|+|B|) bytes per pair.
 #include <math.h>
 
+#include <sched.h>
+
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace panib {
@@ -428,9 +433,32 @@ extern "C" int panib_ani_device(const uint32_t *d_ov, int64_t ld_ov, const int32
 extern "C" int panib_ani_host(const uint32_t *h_ov, int64_t ld_ov, const int32_t *h_q_counts, int64_t nq,
                               const int32_t *h_s_counts, int64_t ns, int k, double *h_identity,
                               double *h_cov_query) {
-    for (int64_t q = 0; q < nq; q++)
-        for (int64_t s = 0; s < ns; s++)
-            pair_ani(h_ov[q * ld_ov + s], h_q_counts[q], h_s_counts[s], k, h_identity[q * ns + s],
-                     h_cov_query[q * ns + s]);
+    // two libm pow per pair: 10^8 pairs at 10,000 genomes, so the query rows are spread over the host threads
+    // the process may use (the values do not depend on the split: every pair is computed independently)
+    auto rows = [&](int64_t q0, int64_t q1) {
+        for (int64_t q = q0; q < q1; q++)
+            for (int64_t s = 0; s < ns; s++)
+                pair_ani(h_ov[q * ld_ov + s], h_q_counts[q], h_s_counts[s], k, h_identity[q * ns + s],
+                         h_cov_query[q * ns + s]);
+    };
+    int threads = 1;
+    if (nq * ns >= (1 << 16)) {
+        cpu_set_t set;
+        threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        if (threads > 64) threads = 64;
+        if (threads > nq) threads = (int)nq;
+        if (threads < 1) threads = 1;
+    }
+    if (threads == 1) {
+        rows(0, nq);
+        return PANIB_OK;
+    }
+    std::vector<std::thread> pool;
+    const int64_t per = (nq + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const int64_t q0 = t * per, q1 = q0 + per < nq ? q0 + per : nq;
+        if (q0 < q1) pool.emplace_back(rows, q0, q1);
+    }
+    for (auto &th : pool) th.join();
     return PANIB_OK;
 }

@@ -659,3 +659,101 @@ extern "C" int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t
                                   seed, max_hash, d_nb, d_bmul, d_table, row_stride, nullptr, d_flags, d_status,
                                   stream, false);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Packed host-buffer form: the ingest pipeline of the drop-in path.  The genomes arrive as an ASCII base
+// stream in host memory (h_ascii) or already packed (h_ascii == NULL).  The stream is cut into chunks of
+// whole tiles; the pool of host threads (hostpack.cpp) packs chunk c+1 into the pinned h_packed / h_mask
+// while chunk c crosses PCIe (0.375 byte per base instead of 1) on the copy stream and chunk c-1 is hashed
+// by K1 on the caller's stream.  d_counts == NULL leaves the rows as bucketed hash sets (the caller
+// finalizes: panib_sketch_finalize or, on several GPUs, panib_sketch_finalize_gather).
+// ------------------------------------------------------------------------------------------------
+namespace panib {
+struct HostPackJob;
+HostPackJob *host_pack_start(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
+                             int64_t bases_per_block, int threads);
+void host_pack_wait_prefix(HostPackJob *hp, int64_t blocks);
+void host_pack_finish(HostPackJob *hp);
+}  // namespace panib
+
+extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_packed, uint32_t *h_mask,
+                                        int64_t n_bases, uint32_t *d_packed, uint32_t *d_mask,
+                                        const int64_t *d_tile_off, int64_t n_genomes, int64_t n_tiles, int k,
+                                        uint32_t seed, uint64_t max_hash, const int32_t *d_nb,
+                                        const uint64_t *d_bmul, uint64_t *d_table, int64_t row_stride,
+                                        int32_t *d_counts, int32_t *d_flags, int32_t *d_status, int host_threads,
+                                        void *stream) {
+    if (n_bases != (n_tiles + 1) * (int64_t)kTileBases) {
+        set_error("n_bases=%lld must equal (n_tiles+1)*%d", (long long)n_bases, kTileBases);
+        return PANIB_E_ARG;
+    }
+    if (!h_packed || !h_mask) {
+        set_error("panib_sketch_packed_host: h_packed / h_mask must be (pinned) host buffers");
+        return PANIB_E_ARG;
+    }
+    int rc = check_sketch_args(k, row_stride);
+    if (rc) return rc;
+    if (n_genomes <= 0 || n_tiles <= 0) return PANIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    constexpr int kMaxChunks = 64;
+    constexpr int64_t kBlockTiles = 64;  // packing block: 64 tiles = 256 Ki bases
+    static thread_local cudaStream_t copy_stream = nullptr;
+    static thread_local cudaEvent_t ev_copied[kMaxChunks], ev_ready = nullptr;
+    static thread_local int ev_device = -1;
+    int dev = 0;
+    PANIB_CUDA(cudaGetDevice(&dev));
+    if (!copy_stream || ev_device != dev) {
+        PANIB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; i++)
+            PANIB_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+        PANIB_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+        ev_device = dev;
+    }
+    // chunks of whole packing blocks, >= 512 tiles (2 Mi bases) each, at most kMaxChunks
+    const int64_t total_tiles = n_tiles + 1;
+    int64_t per = (total_tiles + kMaxChunks - 1) / kMaxChunks;
+    if (per < 512) per = 512;
+    per = (per + kBlockTiles - 1) / kBlockTiles * kBlockTiles;
+    const int n_chunks = (int)((total_tiles + per - 1) / per);
+
+    HostPackJob *job = nullptr;
+    if (h_ascii) job = host_pack_start(h_ascii, n_bases, h_packed, h_mask, kBlockTiles * kTileBases, host_threads);
+    auto fail = [&](int code) {
+        if (job) host_pack_finish(job);
+        return code;
+    };
+#define PANIB_CUDA_JOB(call)                                                      \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) {                                                 \
+            panib::set_error("%s failed: %s", #call, cudaGetErrorString(e__));   \
+            return fail(PANIB_E_CUDA);                                            \
+        }                                                                         \
+    } while (0)
+    PANIB_CUDA_JOB(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
+    PANIB_CUDA_JOB(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
+    // the copy stream must not overwrite d_packed / d_mask while earlier work on `st` may still read them
+    PANIB_CUDA_JOB(cudaEventRecord(ev_ready, st));
+    PANIB_CUDA_JOB(cudaStreamWaitEvent(copy_stream, ev_ready, 0));
+    int64_t hashed = 0;  // tiles [0, hashed) are done
+    for (int c = 0; c < n_chunks; c++) {
+        const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles;
+        if (job) host_pack_wait_prefix(job, (t1 + kBlockTiles - 1) / kBlockTiles);
+        PANIB_CUDA_JOB(cudaMemcpyAsync(d_packed + t0 * (kTileBases / 16), h_packed + t0 * (kTileBases / 16),
+                                       (size_t)(t1 - t0) * (kTileBases / 4), cudaMemcpyHostToDevice, copy_stream));
+        PANIB_CUDA_JOB(cudaMemcpyAsync(d_mask + t0 * (kTileBases / 32), h_mask + t0 * (kTileBases / 32),
+                                       (size_t)(t1 - t0) * (kTileBases / 8), cudaMemcpyHostToDevice, copy_stream));
+        PANIB_CUDA_JOB(cudaEventRecord(ev_copied[c], copy_stream));
+        PANIB_CUDA_JOB(cudaStreamWaitEvent(st, ev_copied[c], 0));
+        const int64_t upto = c == n_chunks - 1 ? n_tiles : t1 - 1;  // halo of tile t1-1 is in the next chunk
+        rc = launch_hash_range(d_packed, d_mask, d_tile_off, n_genomes, hashed, upto, k, seed, max_hash, d_nb,
+                               d_bmul, d_table, row_stride, d_flags, d_status, st);
+        if (rc) return fail(rc);
+        if (upto > hashed) hashed = upto;
+    }
+#undef PANIB_CUDA_JOB
+    if (job) host_pack_finish(job);
+    if (!d_counts) return PANIB_OK;
+    return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, d_status, stream);
+}

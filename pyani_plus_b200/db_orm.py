@@ -402,10 +402,12 @@ class Run:
         return RunComparisons(self)
 
     # ---- cached matrices ----------------------------------------------------------------------
-    def cache_comparisons(self) -> None:
+    def cache_comparisons(self, *, computed: tuple | None = None) -> None:
         """Collect the N x N matrices and cache them as pandas "split" JSON (reference: db_orm.py:393-466).
 
-        Rows = query, columns = subject, both sorted by MD5.  The caller commits.
+        Rows = query, columns = subject, both sorted by MD5.  The caller commits.  ``computed`` =
+        (sorted MD5 list, identity, cov_query) hands over matrices the caller has just recorded for a run
+        that had no comparisons before, which saves reading the N^2 rows back one by one.
         """
         import numpy as np  # noqa: PLC0415
         import pandas as pd  # noqa: PLC0415
@@ -417,7 +419,10 @@ class Run:
         cov_query = np.full([size, size], np.nan, float)
         aln_length = np.full([size, size], np.nan, float)
         sim_errors = np.full([size, size], np.nan, float)
-        if self._session is not None:
+        if computed is not None and list(computed[0]) == hashes:
+            identity[:] = computed[1]
+            cov_query[:] = computed[2]
+        elif self._session is not None:
             sql = ("SELECT comparisons.query_hash, comparisons.subject_hash, comparisons.identity,"
                    " comparisons.cov_query, comparisons.aln_length, comparisons.sim_errors" + _RUN_JOIN)
             for q, s, idn, cov, aln, sim in self._session.execute(
@@ -709,30 +714,56 @@ def insert_comparisons_with_retries(
 
 def insert_comparison_arrays(  # noqa: PLR0913
     logger: logging.Logger, session: Session, configuration_id: int, query_hashes: list[str],
-    subject_hashes: list[str], identity: Any, cov_query: Any,
+    subject_hashes: list[str], identity: Any, cov_query: Any, *, rows_per_commit: int = 2_000_000,
 ) -> bool:
     """Array-backed ``INSERT OR IGNORE`` of a queries x subjects block (NaN -> NULL).
 
-    Same row semantics as ``insert_comparisons_with_retries`` without building one dict per pair:
-    what makes runs of thousands of genomes practical.
+    Same row semantics and the same three-attempt retry as ``insert_comparisons_with_retries`` (reference:
+    db_orm.py:1044-1114), without one dict -- or one Python frame -- per pair: each query row becomes two
+    object arrays (NaN masked to None by numpy) and the parameter tuples come out of ``zip`` / ``repeat``,
+    i.e. C iterators, straight into ``executemany``.  Committed in chunks of whole query rows, so a
+    transient lock costs one chunk, not the run (what makes N = 10,000 practical).
+    Returns False when a chunk could not be recorded after three attempts.
     """
-    import math  # noqa: PLC0415
+    import random  # noqa: PLC0415
+    from itertools import chain, repeat  # noqa: PLC0415
+
+    import numpy as np  # noqa: PLC0415
 
     uname = platform.uname()
-    tail = (uname.system, uname.release, uname.machine)
-
-    def rows():  # noqa: ANN202
-        for i, q in enumerate(query_hashes):
-            id_row, cov_row = identity[i], cov_query[i]
-            for j, s in enumerate(subject_hashes):
-                a, b = float(id_row[j]), float(cov_row[j])
-                yield (q, s, configuration_id, None if math.isnan(a) else a, None, None,
-                       None if math.isnan(b) else b, None, *tail)
-
-    msg = f"Attempting to record {len(query_hashes) * len(subject_hashes)} comparisons."
+    n_q, n_s = len(query_hashes), len(subject_hashes)
+    msg = f"Attempting to record {n_q * n_s} comparisons."
     logger.debug(msg)
     sql = (f"INSERT OR IGNORE INTO comparisons ({', '.join(COMPARISON_COLUMNS)})"  # noqa: S608
            f" VALUES ({', '.join('?' * 11)})")
-    session.executemany(sql, rows())
-    session.commit()
+    identity = np.asarray(identity, dtype=np.float64).reshape(n_q, n_s)
+    cov_query = np.asarray(cov_query, dtype=np.float64).reshape(n_q, n_s)
+
+    def row_params(i: int):  # noqa: ANN202
+        ident = identity[i].astype(object)
+        ident[np.isnan(identity[i])] = None
+        cov = cov_query[i].astype(object)
+        cov[np.isnan(cov_query[i])] = None
+        return zip(repeat(query_hashes[i]), subject_hashes, repeat(configuration_id), ident, repeat(None),
+                   repeat(None), cov, repeat(None), repeat(uname.system), repeat(uname.release),
+                   repeat(uname.machine))
+
+    step = max(1, rows_per_commit // max(1, n_s))
+    for i0 in range(0, n_q, step):
+        i1 = min(n_q, i0 + step)
+        for attempt, pause in ((1, 20 + 10 * random.random()), (2, 30 + 10 * random.random()), (3, 0)):  # noqa: S311
+            try:
+                session.executemany(sql, chain.from_iterable(row_params(i) for i in range(i0, i1)))
+                session.commit()
+            except sqlite3.OperationalError:  # pragma: no cover
+                msg = f"Attempt {attempt}/3 failed to record comparisons of query rows {i0}..{i1}"
+                if attempt < 3:  # noqa: PLR2004
+                    logger.warning(msg)
+                    sleep(pause)
+                else:
+                    logger.critical(msg)
+                    return False
+            else:
+                break
+    logger.debug("Done")
     return True

@@ -26,6 +26,7 @@ PROGRAM = "panib200"  # recorded as Configuration.program (the reference records
 
 ST_BUCKET_OVERFLOW = 1
 ST_SEGMENT_OVERFLOW = 2
+ST_INDEX_OVERFLOW = 4
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -79,6 +80,12 @@ def load_library() -> ctypes.CDLL:
     L.panib_sketch_ascii_host.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp, _vp]
     L.panib_sketch_ascii_host_hash_only.restype = _i32
     L.panib_sketch_ascii_host_hash_only.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp]
+    L.panib_host_threads.restype = _i32
+    L.panib_pack_host.restype = _i32
+    L.panib_pack_host.argtypes = [_vp, _i64, _vp, _vp, _i32]
+    L.panib_sketch_packed_host.restype = _i32
+    L.panib_sketch_packed_host.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _u32, _u64, _vp, _vp,
+                                           _vp, _i64, _vp, _vp, _vp, _i32, _vp]
     L.panib_sketch_finalize_gather.restype = _i32
     L.panib_sketch_finalize_gather.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i32, _i32,
                                                _i64, _vp]
@@ -88,11 +95,13 @@ def load_library() -> ctypes.CDLL:
     L.panib_intersect_fence_entries.restype = _i64
     L.panib_intersect_fence_entries.argtypes = [_i64, _i64, _u64, _i64, _i32, _i32]
     L.panib_index_workspace_bytes.restype = _i32
-    L.panib_index_workspace_bytes.argtypes = [_i64, _i64, _i32, ctypes.POINTER(_i64)]
+    L.panib_index_workspace_bytes.argtypes = [_i64, _i64, _i32, _i32, ctypes.POINTER(_i64)]
     L.panib_index_build.restype = _i32
-    L.panib_index_build.argtypes = [_vp, _vp, _i64, _i64, _u64, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp]
+    L.panib_index_build.argtypes = [_vp, _vp, _i64, _i64, _u64, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _vp,
+                                    _vp, _vp]
     L.panib_index_count.restype = _i32
-    L.panib_index_count.argtypes = [_vp, _i64, _u64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]
+    L.panib_index_count.argtypes = [_vp, _i64, _u64, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32,
+                                    _vp, _vp]
     L.panib_ani_device.restype = _i32
     L.panib_ani_device.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]
     L.panib_ani_host.restype = _i32
@@ -148,6 +157,19 @@ def fasta_to_stream(text: bytes) -> tuple[np.ndarray, int, int, bytes | None]:
             _check(got if got < 0 else -2)
     title = text[out4[2]: out4[2] + out4[3]] if out4[2] >= 0 else None
     return stream, int(out4[0]), int(out4[1]), title
+
+
+def pack_host(ascii_stream: np.ndarray, threads: int = 0) -> tuple[np.ndarray, np.ndarray]:
+    """ASCII base stream -> (packed 2-bit words, validity-mask words) on the library's host threads
+    (``panib_pack_host``: the host form of the device pack kernel; needs no GPU)."""
+    a = np.ascontiguousarray(ascii_stream, dtype=np.uint8)
+    if a.size % 32:
+        msg = "the ASCII stream length must be a multiple of 32"
+        raise ValueError(msg)
+    packed = np.empty(a.size // 16, dtype=np.uint32)
+    mask = np.empty(a.size // 32, dtype=np.uint32)
+    _check(load_library().panib_pack_host(a.ctypes.data, a.size, packed.ctypes.data, mask.ctypes.data, threads))
+    return packed, mask
 
 
 def ani_host(ov: np.ndarray, q_counts: np.ndarray, s_counts: np.ndarray, k: int) -> tuple[np.ndarray, np.ndarray]:
@@ -255,8 +277,13 @@ class Engine:
         return int(st)
 
     # ------------------------------------------------------------------ stage 0+1: sketch
-    def plan_stream(self, tile_off: np.ndarray, scaled: int, slack: float = 1.0) -> "StreamPlan":
-        """Bucket plan + device copies of the per-genome arrays for one tiled base stream."""
+    def plan_stream(self, tile_off: np.ndarray, scaled: int, slack: float = 1.0, *,
+                    row_stride: int | None = None) -> "StreamPlan":
+        """Bucket plan + device copies of the per-genome arrays for one tiled base stream.
+
+        ``row_stride`` forces the table's row stride (a multiple of 1024 slots, at least what this
+        stream needs): ranks whose slices hold genomes of different lengths must agree on ONE stride
+        before their rows are exchanged (``run.agree_row_stride``)."""
         torch = self.torch
         tile_off = np.ascontiguousarray(tile_off, dtype=np.int64)
         n_genomes = len(tile_off) - 1
@@ -271,13 +298,24 @@ class Engine:
         return StreamPlan(
             tile_off=tile_off, n_genomes=n_genomes, n_tiles=int(tile_off[-1]),
             n_bases=(int(tile_off[-1]) + 1) * _stream.TILE, scaled=scaled, max_hash=max_hash(scaled),
-            slack=slack, row_stride=int(nb.max()) * 1024,
+            slack=slack, row_stride=self._checked_stride(int(nb.max()) * 1024, row_stride),
             d_tile_off=torch.from_numpy(tile_off).to(self.device),
             d_nb=torch.from_numpy(nb).to(self.device),
             d_bmul=torch.from_numpy(bmul.view(np.int64)).to(self.device),
         )
 
-    def alloc_stream_buffers(self, plan: "StreamPlan", *, ascii_too: bool = False) -> dict:
+    @staticmethod
+    def _checked_stride(needed: int, forced: int | None) -> int:
+        if forced is None:
+            return needed
+        if forced < needed or forced % 1024:
+            msg = f"row_stride={forced} must be a multiple of 1024 and at least {needed}"
+            raise ValueError(msg)
+        return int(forced)
+
+    def alloc_stream_buffers(self, plan: "StreamPlan", *, ascii_too: bool = False, host_packed: bool = False) -> dict:
+        """Device buffers of the packed stream; ``ascii_too`` adds a device ASCII buffer (device-side pack),
+        ``host_packed`` the pinned host buffers the ingest pipeline packs into (``sketch_host``)."""
         torch = self.torch
         bufs = {
             "packed": torch.empty(plan.n_bases // 16, dtype=torch.int32, device=self.device),
@@ -285,6 +323,9 @@ class Engine:
         }
         if ascii_too:
             bufs["ascii"] = torch.empty(plan.n_bases, dtype=torch.uint8, device=self.device)
+        if host_packed:
+            bufs["h_packed"] = torch.empty(plan.n_bases // 16, dtype=torch.int32, pin_memory=True)
+            bufs["h_mask"] = torch.empty(plan.n_bases // 32, dtype=torch.int32, pin_memory=True)
         return bufs
 
     def alloc_table(self, plan: "StreamPlan") -> dict:
@@ -316,6 +357,19 @@ class Engine:
         """H2D copy of a pinned ASCII stream + pack + K1 in one C-ABI call (enqueue only)."""
         _check(self.lib.panib_sketch_ascii_host(h_ascii.data_ptr(), bufs["ascii"].data_ptr(), plan.n_bases,
                                                 *self._sketch_args(plan, bufs, tab, k, seed)))
+
+    def sketch_host(self, h_ascii, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42,
+                    finalize: bool = True, threads: int = 0) -> None:
+        """The ingest pipeline in one C-ABI call (``panib_sketch_packed_host``): the host threads pack the
+        ASCII stream (a host tensor; ``None`` = ``bufs["h_packed"]`` / ``["h_mask"]`` are already filled)
+        chunk by chunk into the pinned buffers while earlier chunks are copied (0.375 byte per base) and
+        hashed.  Returns when the host work is done and the device work is enqueued; ``finalize=False``
+        leaves the rows bucketed (multi-GPU: ``finalize_gather`` follows)."""
+        a = self._sketch_args(plan, bufs, tab, k, seed)
+        _check(self.lib.panib_sketch_packed_host(
+            h_ascii.data_ptr() if h_ascii is not None else None, bufs["h_packed"].data_ptr(),
+            bufs["h_mask"].data_ptr(), plan.n_bases, *a[:12], a[12] if finalize else None, a[13], a[14], threads,
+            a[15]))
 
     def hash_packed(self, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42) -> None:
         """K1 hashing only: rows are left as bucketed hash sets (finalize separately)."""
@@ -353,18 +407,19 @@ class Engine:
     ) -> SketchTable:
         """Sketch every genome of one tiled ASCII base stream (``stream.py`` layout).
 
-        ``ascii_stream`` is a pinned uint8 torch tensor when ``from_host`` (copied H2D inside the C
-        call), else a device tensor.  Retries with more buckets if a bucket overflowed.
+        ``ascii_stream`` is a host uint8 torch tensor when ``from_host`` (packed on the host threads and
+        copied H2D in packed form inside the C call), else a device tensor.  Retries with more buckets if
+        a bucket overflowed.
         """
         while True:
             plan = self.plan_stream(tile_off, scaled, slack)
             if ascii_stream.numel() != plan.n_bases:
                 msg = f"ASCII stream has {ascii_stream.numel()} bytes, expected {plan.n_bases}"
                 raise ValueError(msg)
-            bufs = self.alloc_stream_buffers(plan, ascii_too=from_host)
+            bufs = self.alloc_stream_buffers(plan, host_packed=from_host)
             tab = self.alloc_table(plan)
             if from_host:
-                self.sketch_ascii_host(ascii_stream, plan, bufs, tab, k, seed=seed)
+                self.sketch_host(ascii_stream, plan, bufs, tab, k, seed=seed)
             else:
                 self.pack(ascii_stream, plan, bufs)
                 self.sketch_packed(plan, bufs, tab, k, seed=seed)
@@ -424,15 +479,30 @@ class Engine:
         counts = torch.cat([p.counts for p in parts])
         return SketchTable(rows, counts, k, scaled)
 
-    def table_from_host(self, sketches: list[np.ndarray], k: int, scaled: int) -> SketchTable:
-        """Upload sorted duplicate-free uint64 sketches (e.g. read back from ``.sig`` files)."""
+    def table_from_host(self, sketches: list[np.ndarray], k: int, scaled: int, *, stride: int | None = None,
+                        rows: int | None = None) -> SketchTable:
+        """Upload sorted duplicate-free uint64 sketches (e.g. read back from ``.sig`` files).
+
+        The kernels rely on every row being strictly ascending and <= max_hash (fence binary search,
+        monotone bucket index, hash-range sharding), and cache files can come from anywhere, so that is
+        checked here.  ``stride`` / ``rows`` pad the table (multi-GPU: all ranks exchange one shape)."""
         torch = self.torch
-        n = len(sketches)
+        n = len(sketches) if rows is None else int(rows)
         max_count = max((len(s) for s in sketches), default=0)
-        stride = max(16, (max_count + 15) // 16 * 16)
+        need = max(16, (max_count + 15) // 16 * 16)
+        if stride is None:
+            stride = need
+        if stride < need or n < len(sketches):
+            msg = f"table_from_host: stride={stride} / rows={n} too small for {len(sketches)} sketches of up to {max_count}"
+            raise ValueError(msg)
+        mh = max_hash(scaled)
         host = np.zeros((n, stride), dtype=np.uint64)
         counts = np.zeros(n, dtype=np.int32)
         for g, s in enumerate(sketches):
+            s = np.asarray(s, dtype=np.uint64)
+            if s.size and (not (s[1:] > s[:-1]).all() or int(s[-1]) > mh):
+                msg = f"sketch {g} is not strictly ascending within 0..max_hash (scaled={scaled}): corrupt cache file?"
+                raise ValueError(msg)
             host[g, : len(s)] = s
             counts[g] = len(s)
         return SketchTable(torch.from_numpy(host.view(np.int64)).to(self.device),
@@ -512,19 +582,19 @@ class Engine:
 
     # cost model of Engine.intersect(method="auto"), seconds per unit on one B200 (measured)
     COST_PROBE_PER_ELEMENT = 0.6e-12   # probing kernel: per pair and per sketch element (both sketches)
-    COST_INDEX_PER_ENTRY = 1.2e-10     # flatten + radix sort + run detection, per (hash, genome) entry
+    COST_INDEX_PER_ENTRY = 0.6e-10     # hash-table insert + classify + emit, per (hash, genome) entry
     COST_INDEX_PER_WORD = 0.8e-12      # AND+POPC kernel: per pair and per 32 bit-matrix columns
     COST_INDEX_PER_RARE_PAIR = 2.0e-11 # atomicAdd expansion of the rare hashes, per pair
 
     def _intersect_indexed(self, q: SketchTable, ov, mh: int, max_count: int, tau: int, rank: int, world: int,  # noqa: ANN001, PLR0913
                            check: bool, auto: bool):  # noqa: ANN202
         """Inverted-index form of the all-vs-all intersection (csrc/index.cu).  Returns ``ov``, or None
-        when ``auto`` decided that the probing kernel is cheaper for this data."""
+        when ``auto`` decided that the probing kernel is cheaper for this data (or the index cannot be used)."""
         torch = self.torch
         n = q.n
-        pairs = n * (n - 1) / 2 / world
-        est_probe = pairs * 2 * max_count * self.COST_PROBE_PER_ELEMENT
-        if auto and est_probe < 3e-4:  # the index has ~10 launches of fixed cost: not worth it
+        all_pairs = n * (n - 1) / 2
+        est_probe = all_pairs / world * 2 * max_count * self.COST_PROBE_PER_ELEMENT
+        if auto and est_probe < 3e-4:  # the index has ~8 launches of fixed cost: not worth it
             return None
         while True:
             cap = max(1, int(max_count))
@@ -541,32 +611,33 @@ class Engine:
                 if total >= (1 << 31) - 512:
                     return None
             need = _i64(0)
-            _check(self.lib.panib_index_workspace_bytes(n, total, tau_, ctypes.byref(need)))
+            _check(self.lib.panib_index_workspace_bytes(n, total, tau_, world, ctypes.byref(need)))
             if check:  # eager calls share one workspace that grows on demand
                 work = self._index_work
                 if work is None or work.numel() < need.value:
                     self._index_work = work = None  # free the old one first
                     self._index_work = work = torch.empty(need.value, dtype=torch.uint8, device=self.device)
             else:  # enqueue-only calls may sit in a captured graph: their workspace is never freed or resized
-                key = (n, total, tau_)
+                key = (n, total, tau_, world)
                 work = self._index_work_fixed.get(key)
                 if work is None:
                     work = self._index_work_fixed[key] = torch.empty(need.value, dtype=torch.uint8,
                                                                      device=self.device)
             stats = self._index_stats
             _check(self.lib.panib_index_build(q.rows.data_ptr(), q.counts.data_ptr(), q.stride, n, mh, cap, total,
-                                              off_ptr, tau_, work.data_ptr(), work.numel(), stats.data_ptr(),
-                                              self.status.data_ptr(), self._stream()))
+                                              off_ptr, tau_, rank, world, work.data_ptr(), work.numel(),
+                                              stats.data_ptr(), self.status.data_ptr(), self._stream()))
             if auto:
-                n_dense, rare_pairs, _, _ = stats.tolist()
-                est_index = (total * self.COST_INDEX_PER_ENTRY + pairs * -(-n_dense // 32) * self.COST_INDEX_PER_WORD
-                             + rare_pairs / world * self.COST_INDEX_PER_RARE_PAIR)
+                n_dense, rare_pairs, _, _ = stats.tolist()  # of this rank's slice of the hash range
+                est_index = (total / world * self.COST_INDEX_PER_ENTRY
+                             + all_pairs * -(-n_dense // 32) * self.COST_INDEX_PER_WORD
+                             + rare_pairs * self.COST_INDEX_PER_RARE_PAIR)
                 self.last_intersect_estimates = {"probe_s": est_probe, "index_s": est_index,
                                                  "frequent_hashes": n_dense, "rare_pairs": rare_pairs}
                 if est_index >= est_probe:
                     return None
-            _check(self.lib.panib_index_count(q.counts.data_ptr(), n, mh, total, tau_, work.data_ptr(), work.numel(),
-                                              stats.data_ptr(), ov.data_ptr(), q.n, rank, world,
+            _check(self.lib.panib_index_count(q.counts.data_ptr(), n, mh, cap, total, off_ptr, tau_, work.data_ptr(),
+                                              work.numel(), stats.data_ptr(), ov.data_ptr(), q.n, rank, world,
                                               self.status.data_ptr(), self._stream()))
             self.last_intersect_method = "index"
             if not check:
@@ -574,6 +645,10 @@ class Engine:
             st = self._read_status()
             if st & ST_BUCKET_OVERFLOW:
                 msg = "a sketch bucket overflowed in an earlier sketch call whose status was not checked"
+                raise EngineError(msg)
+            if st & ST_INDEX_OVERFLOW:
+                msg = ("the hash range is too unevenly filled for the sharded inverted index "
+                       "(one rank's slice holds more than twice its share): use method='probe'")
                 raise EngineError(msg)
             if st & ST_SEGMENT_OVERFLOW:  # a sketch is larger than cap: take the real maximum and redo
                 max_count = int(q.counts.max().item())

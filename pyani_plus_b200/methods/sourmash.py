@@ -37,8 +37,9 @@ MANYSEARCH_HEADER = (
 )
 
 _engine = None
-# sketches written by prepare_genomes in this process, keyed by .sig path -> (mtime_ns, parsed signature):
-# compute_sourmash_tile then skips re-parsing ~90 KB of JSON per genome
+# sketches read or written in this process, keyed by .sig path -> (mtime_ns, parsed signature): nothing is
+# parsed twice in a process, and across processes the binary side-cache (sigfile.read_side_cache) replaces
+# the ~90 KB of JSON per genome
 _sig_memo: dict[Path, tuple[int, dict]] = {}
 SIG_MEMO_MAX = 20_000
 
@@ -60,6 +61,100 @@ def parse_scaled(logger: logging.Logger, extra: str) -> int:
         msg = f"sourmash requires extra setting of the form scaled=<positive integer>, not {extra!r}"
         log_sys_exit(logger, msg)
     return int(match.group(1))  # type: ignore[union-attr]
+
+
+def load_sketch(sig_path: Path, ksize: int | None = None) -> dict:
+    """One cached sketch: from this process's memo, else the binary side-cache, else the ``.sig`` JSON.
+
+    Returns the ``sigfile.read_sig`` dict (``md5sum`` may be "" until someone needs it: see ``sketch_md5``).
+    """
+    st = sig_path.stat()
+    memo = _sig_memo.get(sig_path)
+    if memo is not None and memo[0] == st.st_mtime_ns:
+        return memo[1]
+    sig = sigfile.read_side_cache(sig_path, st)
+    if sig is None or (ksize is not None and sig["ksize"] != ksize):
+        sig = sigfile.read_sig(sig_path, ksize=ksize)
+        sigfile.write_side_cache(sig_path, sig)  # the next process skips the JSON
+    if len(_sig_memo) < SIG_MEMO_MAX:
+        _sig_memo[sig_path] = (st.st_mtime_ns, sig)
+    return sig
+
+
+def sketch_md5(sig: dict) -> str:
+    """sourmash's checksum of a sketch (only the manysearch.csv artefact prints it)."""
+    if not sig.get("md5sum"):
+        sig["md5sum"] = sigfile.sketch_md5sum(sig["hashes"], sig["ksize"])
+    return sig["md5sum"]
+
+
+def sketch_entries(  # noqa: PLR0913
+    logger: logging.Logger, todo: list[tuple[str, Path]], ksize: int, scaled: int, cache: Path,
+) -> Iterator[tuple[str, np.ndarray]]:
+    """Sketch FASTA files on the GPU and write them to the cache; yields (md5, hashes) in ``todo`` order.
+
+    gunzip + FASTA parsing (C, GIL released) run on a thread pool a bounded window ahead; genomes are
+    sketched in batches of ``PREPARE_BATCH_BYTES``; every sketch is written as sourmash ``.sig`` JSON plus
+    the binary side-cache, and remembered for this process.
+    """
+    from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
+
+    from pyani_plus_b200 import engine  # noqa: PLC0415
+
+    max_hash = engine.max_hash(scaled)
+    pending: list[tuple[str, Path, np.ndarray]] = []
+    pending_bytes = 0
+
+    def flush() -> Iterator[tuple[str, np.ndarray]]:
+        nonlocal pending_bytes
+        if pending:
+            table = get_engine().sketch_genomes([recs for _, _, recs in pending], ksize, scaled)
+            for (md5, fasta_filename, _), hashes in zip(pending, table.to_host(), strict=True):
+                sig_path = cache / f"{md5}.sig"
+                sigfile.write_sig(sig_path, filename=str(fasta_filename), name=md5, ksize=ksize,
+                                  max_hash=max_hash, hashes=hashes)
+                sig = {"name": md5, "filename": str(fasta_filename), "ksize": ksize, "seed": 42,
+                       "max_hash": max_hash, "md5sum": "", "hashes": hashes}
+                sigfile.write_side_cache(sig_path, sig)
+                if len(_sig_memo) < SIG_MEMO_MAX:
+                    _sig_memo[sig_path] = (sig_path.stat().st_mtime_ns, sig)
+                yield md5, hashes
+            pending.clear()
+            pending_bytes = 0
+
+    msg = f"Sketching {len(todo)} genomes into '{cache}'"
+    logger.debug(msg)
+    with ThreadPoolExecutor(max_workers=max(1, min(16, utils.available_cores()))) as pool:
+        window = 4 * pool._max_workers  # noqa: SLF001
+        futures = [pool.submit(utils.read_fasta_stream, path) for _, path in todo[:window]]
+        for i, (md5, path) in enumerate(todo):
+            if i + window < len(todo):
+                futures.append(pool.submit(utils.read_fasta_stream, todo[i + window][1]))
+            stream_bytes = futures[i].result()[0]
+            futures[i] = None  # type: ignore[call-overload]
+            pending.append((md5, path, stream_bytes))
+            pending_bytes += int(stream_bytes.size)
+            if pending_bytes >= PREPARE_BATCH_BYTES:
+                yield from flush()
+    yield from flush()
+
+
+def sketches_for(  # noqa: PLR0913
+    logger: logging.Logger, entries: list[tuple[str, str | Path]], ksize: int, scaled: int, cache: Path,
+) -> list[np.ndarray]:
+    """The sketches of ``entries`` = [(md5, FASTA path)], in order: from the cache where a signature
+    exists, computed on the GPU (and cached) where not."""
+    cache.mkdir(exist_ok=True)
+    out: dict[str, np.ndarray] = {}
+    todo = []
+    for md5, path in entries:
+        sig_path = cache / f"{md5}.sig"
+        if sig_path.is_file():
+            out[md5] = load_sketch(sig_path, ksize)["hashes"]
+        else:
+            todo.append((md5, Path(path)))
+    out.update(sketch_entries(logger, todo, ksize, scaled, cache))
+    return [out[md5] for md5, _ in entries]
 
 
 def prepare_genomes(logger: logging.Logger, run: db_orm.Run, cache: Path) -> Iterator[db_orm.RunGenomeAssociation]:
@@ -92,50 +187,15 @@ def prepare_genomes(logger: logging.Logger, run: db_orm.Run, cache: Path) -> Ite
     cache.mkdir(exist_ok=True)
     fasta_dir = Path(run.fasta_directory)
 
-    from pyani_plus_b200 import engine  # noqa: PLC0415
-
-    from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
-
-    max_hash = engine.max_hash(scaled)
-    pending: list[tuple[db_orm.RunGenomeAssociation, Path, np.ndarray]] = []
-    pending_bytes = 0
-
-    def flush() -> Iterator[db_orm.RunGenomeAssociation]:
-        nonlocal pending_bytes
-        if pending:
-            table = get_engine().sketch_genomes([recs for _, _, recs in pending], ksize, scaled)
-            for (entry, fasta_filename, _), hashes in zip(pending, table.to_host(), strict=True):
-                sig_path = cache / f"{entry.genome_hash}.sig"
-                sigfile.write_sig(sig_path, filename=str(fasta_filename), name=entry.genome_hash, ksize=ksize,
-                                  max_hash=max_hash, hashes=hashes)
-                if len(_sig_memo) < SIG_MEMO_MAX:
-                    _sig_memo[sig_path] = (sig_path.stat().st_mtime_ns, {
-                        "name": entry.genome_hash, "filename": str(fasta_filename), "ksize": ksize, "seed": 42,
-                        "max_hash": max_hash, "md5sum": sigfile.sketch_md5sum(hashes, ksize), "hashes": hashes})
-                yield entry
-            pending.clear()
-            pending_bytes = 0
-
-    todo = []
+    todo = {}
     for entry in run.fasta_hashes:
         if (cache / f"{entry.genome_hash}.sig").is_file():
             yield entry
         else:
-            todo.append(entry)
-    # gunzip + FASTA parsing (C, GIL released) on a thread pool, in order, a bounded window ahead
-    with ThreadPoolExecutor(max_workers=max(1, min(16, utils.available_cores()))) as pool:
-        window = 4 * pool._max_workers  # noqa: SLF001
-        futures = [pool.submit(utils.read_fasta_stream, fasta_dir / e.fasta_filename) for e in todo[:window]]
-        for i, entry in enumerate(todo):
-            if i + window < len(todo):
-                futures.append(pool.submit(utils.read_fasta_stream, fasta_dir / todo[i + window].fasta_filename))
-            stream_bytes = futures[i].result()[0]
-            futures[i] = None  # type: ignore[call-overload]
-            pending.append((entry, fasta_dir / entry.fasta_filename, stream_bytes))
-            pending_bytes += int(stream_bytes.size)
-            if pending_bytes >= PREPARE_BATCH_BYTES:
-                yield from flush()
-    yield from flush()
+            todo[entry.genome_hash] = entry
+    work = [(md5, fasta_dir / e.fasta_filename) for md5, e in todo.items()]
+    for md5, _ in sketch_entries(logger, work, ksize, scaled, cache):
+        yield todo[md5]
 
 
 def parse_sourmash_manysearch_csv(
@@ -242,11 +302,7 @@ def tile_arrays(  # noqa: PLR0913
         if not sig_path.is_file():
             msg = f"Missing sourmash signature file '{sig_path}'"
             log_sys_exit(logger, msg)
-        memo = _sig_memo.get(sig_path)
-        if memo is not None and memo[0] == sig_path.stat().st_mtime_ns:
-            loaded[md5] = memo[1]
-        else:
-            loaded[md5] = sigfile.read_sig(sig_path, ksize=int(m.group(1)) if m else None)
+        loaded[md5] = load_sketch(sig_path, int(m.group(1)) if m else None)
     if not loaded:
         empty = np.zeros((0, 0))
         return queries, subjects, empty.astype(np.uint32), empty, empty
@@ -281,12 +337,13 @@ def tile_arrays(  # noqa: PLR0913
     identity, cov_query = engine.ani_host(ov, q_counts, s_counts, ksize)
     if tmp_dir is not None and len(queries) * len(subjects) <= MANYSEARCH_CSV_MAX_ROWS:
         write_manysearch_csv(
-            tmp_dir / "manysearch.csv", queries, subjects, [loaded[h]["md5sum"] for h in queries],
-            [loaded[h]["md5sum"] for h in subjects], q_counts, s_counts, ov, ksize, scaled,
+            tmp_dir / "manysearch.csv", queries, subjects, [sketch_md5(loaded[h]) for h in queries],
+            [sketch_md5(loaded[h]) for h in subjects], q_counts, s_counts, ov, ksize, scaled,
         )
-    for i in np.flatnonzero([q in subject_hashes for q in queries]):  # self-vs-self must be one
-        j = subjects.index(queries[i])
-        if ov[i, j] and identity[i, j] != 1.0:
+    column_of = {s: j for j, s in enumerate(subjects)}
+    for i, q in enumerate(queries):  # self-vs-self must be one
+        j = column_of.get(q)
+        if j is not None and ov[i, j] and identity[i, j] != 1.0:
             msg = f"Expected sourmash manysearch {queries[i]} vs self to be one, not {identity[i, j]!r}"
             raise ValueError(msg)
     return queries, subjects, ov, identity, cov_query

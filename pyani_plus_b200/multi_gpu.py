@@ -47,7 +47,9 @@ def all_gather_tables(rows, counts, world: int, *, sizes_in_last_slot: bool = Tr
 
     The sketch-finalize kernel stores every row's size in the row's last slot, so ONE collective
     moves sketches and sizes together (``sizes_in_last_slot``); otherwise the sizes are gathered by
-    a second, tiny collective.
+    a second, tiny collective.  Every rank must pass the same shape: callers establish that once, when
+    they set the exchange up (``assert_same_shape`` -- it synchronises, so it cannot live in here, where a
+    CUDA graph may be capturing).
     """
     if world == 1:
         return rows, counts
@@ -62,6 +64,35 @@ def all_gather_tables(rows, counts, world: int, *, sizes_in_last_slot: bool = Tr
         all_counts = torch.empty(world * counts.shape[0], dtype=counts.dtype, device=counts.device)
         dist.all_gather_into_tensor(all_counts, counts.contiguous())
     return all_rows, all_counts
+
+
+def agree_max(value: int, world: int, device=None) -> int:  # noqa: ANN001
+    """MAX of an integer over the ranks (row strides, size hints: every rank must use the same one)."""
+    if world == 1:
+        return int(value)
+    import torch  # noqa: PLC0415
+    import torch.distributed as dist  # noqa: PLC0415
+
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+def assert_same_shape(rows) -> None:  # noqa: ANN001
+    """Every rank must hand the exchange rows of ONE shape: a rank-local stride (each rank plans its own
+    genome slice) would make peers write / read rows at the wrong offsets."""
+    import torch  # noqa: PLC0415
+    import torch.distributed as dist  # noqa: PLC0415
+
+    shape = torch.tensor([rows.shape[0], rows.shape[1], -rows.shape[0], -rows.shape[1]], dtype=torch.int64,
+                         device=rows.device)
+    dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+    lo = (-shape[2:]).tolist()
+    hi = shape[:2].tolist()
+    if lo != hi:
+        msg = (f"ranks disagree on the sketch-table shape (rows x stride between {lo} and {hi}): agree on the "
+               "row stride first (run.agree_row_stride / Engine.plan_stream(row_stride=...))")
+        raise ValueError(msg)
 
 
 class SymmetricGather:
@@ -90,12 +121,36 @@ class SymmetricGather:
             raise RuntimeError(msg)
 
     @classmethod
-    def create(cls, per_rank: int, stride: int, world: int, rank: int, device):  # noqa: ANN001, ANN206
-        """The gather object, or None when symmetric memory is unavailable on this system."""
+    def create(cls, per_rank: int, stride: int, world: int, rank: int, device, *,  # noqa: ANN001, ANN206
+               allow_nccl: bool = False, logger=None):  # noqa: ANN001
+        """The gather object.  All ranks must pass the same ``per_rank`` / ``stride`` (checked).
+
+        A failure to set symmetric memory up is an error: it is logged and re-raised, unless the caller
+        explicitly accepts the plain NCCL all-gather as the exchange (``allow_nccl``, what
+        ``--nccl-gather`` asks for), in which case None is returned on EVERY rank if any rank failed."""
+        import torch  # noqa: PLC0415
+        import torch.distributed as dist  # noqa: PLC0415
+
+        if agree_max(stride, world, device) != stride or agree_max(-stride, world, device) != -stride or \
+                agree_max(per_rank, world, device) != per_rank:
+            msg = f"rank {rank}: per_rank={per_rank} / stride={stride} differ between ranks"
+            raise ValueError(msg)
+        err = None
+        obj = None
         try:
-            return cls(per_rank, stride, world, rank, device)
-        except Exception:  # noqa: BLE001
+            obj = cls(per_rank, stride, world, rank, device)
+        except Exception as exc:  # noqa: BLE001
+            err = exc
+            if logger is not None:
+                logger.warning("symmetric-memory gather unavailable on rank %d: %s", rank, exc)
+        ok = torch.tensor([0 if err else 1], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()):
+            return obj
+        if allow_nccl:
             return None
+        msg = "symmetric-memory gather could not be set up on every rank (pass nccl_gather to use NCCL)"
+        raise RuntimeError(msg) from err
 
     def gather(self, eng, plan, tab: dict):  # noqa: ANN001, ANN201
         """Finalize this rank's rows and scatter them to all ranks; returns (all_rows, all_counts)."""

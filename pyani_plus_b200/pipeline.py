@@ -21,7 +21,8 @@ class SourmashStep:
     """One pass of the hot path for a planned stream on this rank."""
 
     def __init__(self, eng, plan, bufs: dict, tab: dict, k: int, *, world: int = 1, rank: int = 0,  # noqa: ANN001, PLR0913
-                 gather=None, size_hint: int | None = None, h_ascii=None, k2_method: str = "auto") -> None:  # noqa: ANN001
+                 gather=None, size_hint: int | None = None, h_ascii=None, k2_method: str = "auto",  # noqa: ANN001
+                 host_threads: int = 0) -> None:
         """``gather`` is a ``multi_gpu.SymmetricGather`` (fused finalize + all-gather) or None (NCCL
         all-gather when ``world > 1``); ``h_ascii`` the pinned ASCII stream for host-input steps;
         ``k2_method`` as in ``Engine.intersect`` -- ``"auto"`` is resolved ONCE, on the first step, from
@@ -31,6 +32,7 @@ class SourmashStep:
         self.world, self.rank, self.gather = world, rank, gather
         self.size_hint = plan.sketch_size_hint() if size_hint is None else size_hint
         self.h_ascii = h_ascii
+        self.host_threads = host_threads  # host-input steps: threads of the ingest pool to use (0 = all)
         self.out: dict = {}
         self._graphs: dict = {}
         self._pinned: dict = {}
@@ -46,13 +48,10 @@ class SourmashStep:
         from . import multi_gpu  # noqa: PLC0415
 
         eng, plan, bufs, tab, k = self.eng, self.plan, self.bufs, self.tab, self.k
-        if self.gather is not None:
-            if from_host:
-                eng.hash_ascii_host(self.h_ascii, plan, bufs, tab, k)
-            else:
-                eng.hash_packed(plan, bufs, tab, k)
-        elif from_host:
-            eng.sketch_ascii_host(self.h_ascii, plan, bufs, tab, k)
+        if from_host:  # ingest pipeline: host threads pack, packed chunks cross PCIe, K1 follows chunk by chunk
+            eng.sketch_host(self.h_ascii, plan, bufs, tab, k, finalize=self.gather is None, threads=self.host_threads)
+        elif self.gather is not None:
+            eng.hash_packed(plan, bufs, tab, k)
         else:
             eng.sketch_packed(plan, bufs, tab, k)
         if marks is not None:
@@ -112,6 +111,8 @@ class SourmashStep:
         and agree on the outcome before replaying (see ``bench.py``)."""
         torch = self.eng.torch
         key = (from_host, to_host)
+        if from_host:  # the host threads pack inside the step: a replayed graph would skip that work
+            return False
         self.run(from_host=from_host, to_host=to_host)  # sets kernel attributes, allocates pinned buffers
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()

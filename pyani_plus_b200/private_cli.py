@@ -22,7 +22,6 @@ import signal
 import sys
 import tempfile
 from contextlib import nullcontext
-from itertools import batched
 from pathlib import Path
 from typing import Annotated
 
@@ -72,127 +71,99 @@ def _check_tool_version(
 # ---------------------------------------------------------------------------------------------
 # JSON hand-over between the compute step and the database (schema: SURVEY.md 3.4)
 # ---------------------------------------------------------------------------------------------
+_CONFIG_FIELDS = ("method", "program", "version", "fragsize", "mode", "kmersize", "minmatch", "extra")
+_CONFIG_REQUIRED = ("method", "program", "version")
+_ROW_REQUIRED = ("query_hash", "subject_hash", "identity")
+_ROW_OPTIONAL = ("aln_length", "sim_errors", "cov_query")
+_ROW_PRIVATE = ("configuration_id", "uname_system", "uname_release", "uname_machine")  # implied by the envelope
+
+
 def export_json_db_entries(
     logger: logging.Logger,
     json_filename: Path,
     configuration: db_orm.Configuration,
     db_entries: list[dict[str, str | float | int | None]],
 ) -> None:
-    """Serialise DB entries for recording in JSON for later import.
+    """Write comparisons as the JSON hand-over file (schema: reference private_cli.py:454-504).
 
-    The entries must all belong to the given configuration and to this machine (uname).
+    One envelope per file: the configuration the rows belong to, this machine's uname, and the rows with the
+    per-row copies of those two dropped.
     """
-    uname = platform.uname()
-    unwanted = {"configuration_id", "uname_system", "uname_release", "uname_machine"}
-    payload = {
-        "configuration": {
-            "method": configuration.method,
-            "program": configuration.program,
-            "version": configuration.version,
-            "fragsize": configuration.fragsize,
-            "mode": configuration.mode,
-            "kmersize": configuration.kmersize,
-            "minmatch": configuration.minmatch,
-            "extra": configuration.extra,
-        },
-        "uname": {"system": uname.system, "release": uname.release, "machine": uname.machine},
-        "comparisons": [{k: v for k, v in e.items() if k not in unwanted} for e in db_entries],
+    host = platform.uname()
+    envelope = {
+        "configuration": {field: getattr(configuration, field) for field in _CONFIG_FIELDS},
+        "uname": {"system": host.system, "release": host.release, "machine": host.machine},
+        "comparisons": [{k: v for k, v in row.items() if k not in _ROW_PRIVATE} for row in db_entries],
     }
-    with json_filename.open("w") as handle:
-        handle.write(_json.dumps(payload))
+    json_filename.write_text(_json.dumps(envelope))
     msg = f"Saved {len(db_entries)} comparisons to {json_filename}"
     logger.debug(msg)
 
 
-def import_json_comparisons(logger: logging.Logger, session: Session, json_filename: Path) -> int:  # noqa: PLR0915
-    """Import a JSON file of comparisons into the database (INSERT OR IGNORE)."""
-    msg = f"Importing {json_filename}"
-    logger.debug(msg)
-    with json_filename.open("rb") as handle:
-        raw = handle.read()
+def _json_envelope(logger: logging.Logger, session: Session, json_filename: Path) -> tuple[dict, dict, list] | None:
+    """Parse and shape-check a hand-over file: (configuration, uname, rows), or None for an empty file.
+
+    Every malformed input ends the program with the reference's message for that case.
+    """
+    raw = json_filename.read_bytes()
     if not raw:
         msg = f"JSON file '{json_filename}' is empty"
         logger.debug(msg)
-        return 0
+        return None
     try:
         data = _json.loads(raw)
     except ValueError:
         logger.exception("Unable to parse JSON:")
-        msg = f"JSON file '{json_filename}' invalid"
-        log_sys_exit(logger, msg)
-    del raw
-    if (
-        not isinstance(data, dict)
-        or not isinstance(data.get("configuration"), dict)
-        or not isinstance(data.get("uname"), dict)
-        or not isinstance(data.get("comparisons"), list)
-    ):
-        msg = f"JSON file '{json_filename}' does not use the expected structure"
-        log_sys_exit(logger, msg)
-    configuration = data["configuration"]
-    comparisons = data["comparisons"]
-    try:
-        uname_system = data["uname"]["system"]
-        uname_release = data["uname"]["release"]
-        uname_machine = data["uname"]["machine"]
-    except KeyError:
-        msg = f"JSON file '{json_filename}' uname incomplete"
-        session.close()
-        log_sys_exit(logger, msg)
-    del data
+        log_sys_exit(logger, f"JSON file '{json_filename}' invalid")
+    shape = {"configuration": dict, "uname": dict, "comparisons": list}
+    if not isinstance(data, dict) or any(not isinstance(data.get(k), t) for k, t in shape.items()):
+        log_sys_exit(logger, f"JSON file '{json_filename}' does not use the expected structure")
+    problems = (
+        ("uname incomplete", data["uname"], ("system", "release", "machine")),
+        ("configuration incomplete", data["configuration"], _CONFIG_REQUIRED),
+    )
+    for what, mapping, keys in problems:
+        if any(k not in mapping for k in keys):
+            session.close()
+            log_sys_exit(logger, f"JSON file '{json_filename}' {what}")
+    return data["configuration"], data["uname"], data["comparisons"]
+
+
+def import_json_comparisons(logger: logging.Logger, session: Session, json_filename: Path) -> int:
+    """Record the comparisons of a hand-over file in the database (INSERT OR IGNORE); returns how many
+    the file held.  The configuration must already be in the database (reference private_cli.py:507-614)."""
+    msg = f"Importing {json_filename}"
+    logger.debug(msg)
+    envelope = _json_envelope(logger, session, json_filename)
+    if envelope is None:
+        return 0
+    configuration, uname, rows = envelope
     try:
         config_id = db_orm.db_configuration(
-            session=session,
-            method=configuration["method"],
-            program=configuration["program"],
-            version=configuration["version"],
-            fragsize=configuration.get("fragsize", None),
-            mode=configuration.get("mode", None),
-            kmersize=configuration.get("kmersize", None),
-            minmatch=configuration.get("minmatch", None),
-            extra=configuration.get("extra", None),
-            create=False,
+            session, *(configuration.get(field) for field in _CONFIG_FIELDS), create=False
         ).configuration_id
-    except KeyError:
-        msg = f"JSON file '{json_filename}' configuration incomplete"
-        session.close()
-        log_sys_exit(logger, msg)
     except NoResultFound:
-        msg = f"JSON file '{json_filename}' configuration not in database"
         session.close()
-        log_sys_exit(logger, msg)
+        log_sys_exit(logger, f"JSON file '{json_filename}' configuration not in database")
     msg = f"Configuration identifier {config_id} in database"
     logger.debug(msg)
-    if not comparisons:
-        msg = f"JSON file '{json_filename}' has no comparisons"
+    if not rows:
         session.close()
+        msg = f"JSON file '{json_filename}' has no comparisons"
         logger.warning(msg)
         return 0
-    try:
-        db_entries = [
-            {
-                "query_hash": row["query_hash"],
-                "subject_hash": row["subject_hash"],
-                "identity": row["identity"],
-                "aln_length": row.get("aln_length", None),
-                "sim_errors": row.get("sim_errors", None),
-                "cov_query": row.get("cov_query", None),
-                "configuration_id": config_id,
-                "uname_system": uname_system,
-                "uname_release": uname_release,
-                "uname_machine": uname_machine,
-            }
-            for row in comparisons
-        ]
-    except KeyError:
-        msg = f"JSON file '{json_filename}' comparison(s) incomplete"
+    if any(key not in row for row in rows for key in _ROW_REQUIRED):
         session.close()
-        log_sys_exit(logger, msg)
+        log_sys_exit(logger, f"JSON file '{json_filename}' comparison(s) incomplete")
+    shared = {"configuration_id": config_id, "uname_system": uname["system"], "uname_release": uname["release"],
+              "uname_machine": uname["machine"]}
+    db_entries = [
+        {**shared, **{k: row[k] for k in _ROW_REQUIRED}, **{k: row.get(k) for k in _ROW_OPTIONAL}} for row in rows
+    ]
     if not db_orm.insert_comparisons_with_retries(logger, session, db_entries, source=str(json_filename)):
-        msg = f"Failed to record '{json_filename}' comparisons to database"  # pragma: no cover
         session.close()  # pragma: no cover
-        log_sys_exit(logger, msg)  # pragma: no cover
-    return len(comparisons)
+        log_sys_exit(logger, f"Failed to record '{json_filename}' comparisons to database")  # pragma: no cover
+    return len(rows)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -416,7 +387,38 @@ def compute_column(  # noqa: C901, PLR0912, PLR0913, PLR0915
     )
 
 
-def run_compute_column(  # noqa: C901, PLR0912, PLR0913, PLR0915
+def resolve_subject(  # noqa: PLR0913
+    logger: logging.Logger, run_id: int, method: str, hash_to_filename: dict[str, str],
+    filename_to_hash: dict[str, str], subject: str,
+) -> tuple[int, str]:
+    """What ``--subject`` names: (one-based column over the sorted MD5s, MD5), or (0, "") for "all columns".
+
+    Accepted, in this order: an MD5 of the run, a FASTA filename of the run (any directory part ignored),
+    a column number (reference private_cli.py:839-866).
+    """
+    ordered = sorted(hash_to_filename)
+    subject_hash = subject if subject in hash_to_filename else filename_to_hash.get(Path(subject).name)
+    if subject_hash is not None:
+        return ordered.index(subject_hash) + 1, subject_hash
+    if not subject.lstrip("+-").isdigit():
+        log_sys_exit(
+            logger, f"Did not recognise {subject!r} as an MD5 hash, filename, or column number in run-id {run_id}"
+        )
+    column = int(subject)
+    if 1 <= column <= len(ordered):
+        return column, ordered[column - 1]
+    if column != 0:
+        log_sys_exit(
+            logger,
+            f"Single column should be in range 1 to {len(ordered)},"
+            f" or for some methods {0} meaning all columns, but not {subject}",
+        )
+    if method != "sourmash":
+        log_sys_exit(logger, "All columns currently only implemented for sourmash")
+    return 0, ""
+
+
+def run_compute_column(  # noqa: PLR0913
     logger: logging.Logger,
     database: Path,
     run_id: int,
@@ -431,95 +433,68 @@ def run_compute_column(  # noqa: C901, PLR0912, PLR0913, PLR0915
     msg = f"Starting compute-column for {subject} to {json}"
     logger.debug(msg)
     if database != ":memory:" and not Path(database).is_file():
-        msg = f"Database '{database}' does not exist"
-        log_sys_exit(logger, msg)
+        log_sys_exit(logger, f"Database '{database}' does not exist")
 
     with db_orm.connect_to_db(logger, database) as session:
         try:
             run = session.get_run(run_id)
         except NoResultFound:
-            msg = f"Database has no run-id {run_id}. Use the list-runs command for more information."
-            log_sys_exit(logger, msg)
-        config = run.configuration
-        method = config.method
-        filename_to_hash = {_.fasta_filename: _.genome_hash for _ in run.fasta_hashes}
-        hash_to_filename = {_.genome_hash: _.fasta_filename for _ in run.fasta_hashes}
-        n = len(hash_to_filename)
-
-        if subject in hash_to_filename:
-            subject_hash = subject
-            column = sorted(hash_to_filename).index(subject_hash) + 1
-        elif Path(subject).name in filename_to_hash:
-            subject_hash = filename_to_hash[Path(subject).name]
-            column = sorted(hash_to_filename).index(subject_hash) + 1
-        else:
-            try:
-                column = int(subject)
-            except ValueError:
-                msg = f"Did not recognise {subject!r} as an MD5 hash, filename, or column number in run-id {run_id}"
-                log_sys_exit(logger, msg)
-            if 0 < column <= n:
-                subject_hash = sorted(hash_to_filename)[column - 1]
-            elif column == 0:
-                if method == "sourmash":
-                    subject_hash = ""
-                else:
-                    msg = "All columns currently only implemented for sourmash"
-                    log_sys_exit(logger, msg)
-            else:
-                msg = (
-                    f"Single column should be in range 1 to {n},"
-                    f" or for some methods {0} meaning all columns, but not {subject}"
-                )
-                log_sys_exit(logger, msg)
-
+            log_sys_exit(
+                logger, f"Database has no run-id {run_id}. Use the list-runs command for more information."
+            )
+        method = run.configuration.method
+        links = list(run.fasta_hashes)
+        filename_to_hash = {link.fasta_filename: link.genome_hash for link in links}
+        hash_to_filename = {link.genome_hash: link.fasta_filename for link in links}
+        column, subject_hash = resolve_subject(logger, run_id, method, hash_to_filename, filename_to_hash, subject)
         if relog is not None:
             logger = relog(column)
         msg = f"Logging {method} compute-column {column}"
         logger.info(msg)
 
-        if column == 0:
-            query_hashes = {_.genome_hash: _.length for _ in run.genomes}  # assume all needed
-        else:
-            missing = set(hash_to_filename).difference(
-                comp.query_hash for comp in run.comparisons().where_subject(subject_hash)
-            )
-            query_hashes = {_.genome_hash: _.length for _ in run.genomes if _.genome_hash in missing}
+        # column 0 = everything; a single column only needs the queries it does not have yet
+        wanted = set(hash_to_filename)
+        if column:
+            wanted -= {comp.query_hash for comp in run.comparisons().where_subject(subject_hash)}
+        query_hashes = {g.genome_hash: g.length for g in run.genomes if g.genome_hash in wanted}
         if not query_hashes:
             msg = f"No {method} comparisons needed against {subject_hash}"
             logger.info(msg)
             return 0
-
-        try:
-            compute = {"sourmash": compute_sourmash}[method]
-        except KeyError:
-            msg = f"Unknown method {method} for run-id {run_id} in {database}"
-            log_sys_exit(logger, msg)
+        if method != "sourmash":
+            log_sys_exit(logger, f"Unknown method {method} for run-id {run_id} in {database}")
 
         fasta_dir = Path(run.fasta_directory)
         if not fasta_dir.is_absolute():
             fasta_dir = (Path(database).parent / fasta_dir).absolute()
         msg = f"FASTA folder {fasta_dir}"
         logger.debug(msg)
-
-        tmp: Path | None = None if temp == Path("-") else temp
-        if tmp:
-            tmp = tmp / f"c{column}"  # avoid worries about name clashes
-            tmp.mkdir(exist_ok=True)
-            msg = f"Using temp folder {tmp}"
-            logger.debug(msg)
-        msg = (
-            f"Calling {method} for {len(query_hashes)} queries"
-            if column == 0
-            else f"Calling {method} for {len(query_hashes)} queries vs {subject_hash}."
-        )
+        msg = f"Calling {method} for {len(query_hashes)} queries" + ("" if column == 0 else f" vs {subject_hash}.")
         logger.info(msg)
 
-        with nullcontext(tmp) if tmp else tempfile.TemporaryDirectory() as tmp_dir:
-            return compute(
+        if temp == Path("-"):
+            workdir = tempfile.TemporaryDirectory()
+        else:
+            kept = temp / f"c{column}"  # one folder per column: no name clashes between workers
+            kept.mkdir(exist_ok=True)
+            msg = f"Using temp folder {kept}"
+            logger.debug(msg)
+            workdir = nullcontext(kept)
+        with workdir as tmp_dir:
+            return compute_sourmash(
                 logger, Path(tmp_dir), session, run, json, fasta_dir, hash_to_filename, filename_to_hash,
                 query_hashes, subject_hash, cache=cache,
             )
+
+
+def _signature_cache(logger: logging.Logger, configuration: db_orm.Configuration, cache: Path) -> Path:
+    """The run's signature directory under ``cache``; it must exist (prepare-genomes makes it)."""
+    sig_cache = cache / f"sourmash_k={configuration.kmersize}_{configuration.extra}"
+    if not sig_cache.is_dir():
+        log_sys_exit(
+            logger, f"Missing sourmash signatures directory '{sig_cache}' - check cache setting '{cache}'."
+        )
+    return sig_cache
 
 
 def compute_sourmash(  # noqa: PLR0913, PLR0917
@@ -536,53 +511,35 @@ def compute_sourmash(  # noqa: PLR0913, PLR0917
     *,
     cache: Path = Path(),
 ) -> int:
-    """Run many-vs-subject (or all-vs-all when ``subject_hash == ""``) for sourmash and log to JSON.
+    """Queries vs one subject -- or all-vs-all when ``subject_hash == ""`` -- for sourmash, logged to JSON.
 
-    Maps identity := max-containment ANI, cov_query := query-containment ANI (reference :1875-1887).
+    identity := max-containment ANI, cov_query := query-containment ANI (reference private_cli.py:1875-1887).
+    The GPU answers the whole block at once, so the rows are collected in one pass and the file is written
+    once (the reference re-dumps it after every 100,000 rows of a slow subprocess).
     """
-    uname = platform.uname()
     configuration = run.configuration
     tool = tools.get_sourmash()
     _check_tool_version(logger, tool, configuration)
-    config_id = configuration.configuration_id
+    sig_cache = _signature_cache(logger, configuration, cache)
 
     from pyani_plus_b200.methods import sourmash  # noqa: PLC0415
 
-    sig_cache = cache / f"sourmash_k={configuration.kmersize}_{configuration.extra}"
-    if not sig_cache.is_dir():
-        msg = f"Missing sourmash signatures directory '{sig_cache}' - check cache setting '{cache}'."
-        log_sys_exit(logger, msg)
-
+    host = platform.uname()
+    shared = {"configuration_id": configuration.configuration_id, "uname_system": host.system,
+              "uname_release": host.release, "uname_machine": host.machine}
+    subjects = {subject_hash} if subject_hash else set(query_hashes)
     db_entries: list[dict[str, str | float | int | None]] = []
     try:
-        for batch in batched(
-            sourmash.compute_sourmash_tile(
-                logger, tool, {subject_hash} if subject_hash else set(query_hashes), set(query_hashes),
-                sig_cache, tmp_dir,
-            ),
-            100000,
-        ):
-            logger.debug("Computed batch, about to log to database.")
-            db_entries.extend(
-                {
-                    "query_hash": q,
-                    "subject_hash": s,
-                    "identity": max_containment,
-                    "cov_query": q_containment,
-                    "configuration_id": config_id,
-                    "uname_system": uname.system,
-                    "uname_release": uname.release,
-                    "uname_machine": uname.machine,
-                }
-                for q, s, q_containment, max_containment in batch
-            )
+        db_entries.extend(
+            {"query_hash": q, "subject_hash": s, "identity": max_containment, "cov_query": q_containment, **shared}
+            for q, s, q_containment, max_containment in sourmash.compute_sourmash_tile(
+                logger, tool, subjects, set(query_hashes), sig_cache, tmp_dir)
+        )
     except KeyboardInterrupt:  # pragma: no cover
         msg = f"Interrupted with {len(db_entries)} completed sourmash comparisons"
         logger.error(msg)  # noqa: TRY400
         run.status = "Worker interrupted"
         session.commit()
-    # (the reference re-dumps the whole JSON after every 100k rows; the GPU finishes all N^2 pairs
-    # before the first row is yielded, so one dump at the end records the same file)
     try:
         export_json_db_entries(logger, json_filename, configuration, db_entries)
     except Exception:  # pragma: no cover  # noqa: BLE001
@@ -591,31 +548,83 @@ def compute_sourmash(  # noqa: PLR0913, PLR0917
     return 0
 
 
-def compute_sourmash_bulk(logger: logging.Logger, session: Session, run: db_orm.Run, cache: Path) -> int:
-    """All-vs-all for the whole run, recorded straight from arrays (no per-pair dict, no JSON).
+def compute_sourmash_block(  # noqa: PLR0913
+    logger: logging.Logger, session: Session, run: db_orm.Run, cache: Path, queries: set[str], subjects: set[str],
+) -> tuple[list[str], list[str], object, object]:
+    """One queries x subjects block recorded straight from arrays (no per-pair dict, no JSON).
 
-    Same row semantics as ``compute_sourmash`` + ``import_json_comparisons`` (N^2 ordered rows,
-    identity := max-containment ANI, cov_query := query-containment ANI, NULL where there is no common
-    hash, INSERT OR IGNORE), for runs too large for the dict / JSON hand-over.
-    Returns the number of ordered pairs computed.
+    Same row semantics as ``compute_sourmash`` + ``import_json_comparisons`` (ordered rows, identity :=
+    max-containment ANI, cov_query := query-containment ANI, NULL where there is no common hash, INSERT OR
+    IGNORE).  ``queries == subjects`` is the all-vs-all call (inverted-index or probing K2, chosen from the
+    data); anything else is a rectangular call served by the probing kernel -- what ``resume`` uses to
+    compute only what a partial run lacks (reference private_cli.py:879-898).
+    Returns (sorted queries, sorted subjects, identity, cov_query).
     """
     configuration = run.configuration
-    tool = tools.get_sourmash()
-    _check_tool_version(logger, tool, configuration)
+    _check_tool_version(logger, tools.get_sourmash(), configuration)
+    sig_cache = _signature_cache(logger, configuration, cache)
 
     from pyani_plus_b200.methods import sourmash  # noqa: PLC0415
 
-    sig_cache = cache / f"sourmash_k={configuration.kmersize}_{configuration.extra}"
-    if not sig_cache.is_dir():
-        msg = f"Missing sourmash signatures directory '{sig_cache}' - check cache setting '{cache}'."
-        log_sys_exit(logger, msg)
-    hashes = {_.genome_hash for _ in run.fasta_hashes}
-    queries, subjects, _, identity, cov_query = sourmash.tile_arrays(logger, hashes, hashes, sig_cache, None)
-    if not db_orm.insert_comparison_arrays(logger, session, configuration.configuration_id, queries, subjects,
+    q_sorted, s_sorted, _, identity, cov_query = sourmash.tile_arrays(logger, subjects, queries, sig_cache, None)
+    if not db_orm.insert_comparison_arrays(logger, session, configuration.configuration_id, q_sorted, s_sorted,
                                            identity, cov_query):
-        msg = "Failed to record comparisons to database"  # pragma: no cover
-        log_sys_exit(logger, msg)  # pragma: no cover
-    return len(queries) * len(subjects)
+        log_sys_exit(logger, "Failed to record comparisons to database")  # pragma: no cover
+    return q_sorted, s_sorted, identity, cov_query
+
+
+def compute_sourmash_bulk(logger: logging.Logger, session: Session, run: db_orm.Run, cache: Path) -> int:
+    """All-vs-all for the whole run through ``compute_sourmash_block``; returns the
+    number of ordered pairs computed."""
+    hashes = {link.genome_hash for link in run.fasta_hashes}
+    fresh = run.comparisons().count() == 0
+    q_sorted, s_sorted, identity, cov_query = compute_sourmash_block(logger, session, run, cache, hashes, hashes)
+    if fresh:  # the matrices just recorded ARE the run's matrices: no need to read N^2 rows back
+        run.cache_comparisons(computed=(q_sorted, identity, cov_query))
+    return len(q_sorted) * len(s_sorted)
+
+
+def missing_block(run: db_orm.Run) -> tuple[set[str], set[str]]:
+    """The smallest queries x subjects block that covers every comparison the run still lacks."""
+    hashes = sorted(link.genome_hash for link in run.fasta_hashes)
+    have: dict[str, set[str]] = {h: set() for h in hashes}
+    for comp in run.comparisons():
+        have[comp.subject_hash].add(comp.query_hash)
+    everyone = set(hashes)
+    subjects = {s for s, qs in have.items() if len(qs) < len(hashes)}
+    queries = set().union(*(everyone - have[s] for s in subjects)) if subjects else set()
+    return queries, subjects
+
+
+def compute_sourmash_distributed(  # noqa: PLR0913
+    logger: logging.Logger, session: Session | None, run_job: dict, cache: Path, ctx, run: db_orm.Run | None = None,  # noqa: ANN001
+) -> int:
+    """All-vs-all over every rank of a ``torchrun`` launch (``run.all_vs_all_files``): each rank sketches a
+    slice of the genomes (honouring the shared ``.sig`` cache), the sketches are exchanged once, the pair work
+    is sharded, and rank 0 -- the only rank with a database session -- records the N^2 rows.
+
+    ``run_job`` is the picklable description rank 0 broadcasts: entries [(md5, FASTA path)], ksize, scaled,
+    sig cache directory.  Returns the number of ordered pairs (0 on the other ranks).
+    """
+    from pyani_plus_b200 import run as run_mod  # noqa: PLC0415
+
+    sig_cache = Path(run_job["sig_cache"])
+    if ctx.rank == 0:
+        sig_cache.mkdir(parents=True, exist_ok=True)
+    ctx.barrier()
+    result = run_mod.all_vs_all_files(logger, ctx, [tuple(e) for e in run_job["entries"]], run_job["ksize"],
+                                      run_job["scaled"], sig_cache)
+    if ctx.rank != 0 or result is None:
+        return 0
+    hashes, _, _, identity, cov_query = result
+    assert session is not None and run is not None  # noqa: S101
+    fresh = run.comparisons().count() == 0
+    if not db_orm.insert_comparison_arrays(logger, session, run.configuration.configuration_id, hashes, hashes,
+                                           identity, cov_query):
+        log_sys_exit(logger, "Failed to record comparisons to database")  # pragma: no cover
+    if fresh:
+        run.cache_comparisons(computed=(hashes, identity, cov_query))
+    return len(hashes) ** 2
 
 
 if __name__ == "__main__":

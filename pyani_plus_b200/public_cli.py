@@ -23,6 +23,7 @@ import typer
 from rich.progress import Progress
 
 from pyani_plus_b200 import LOG_FILE, LOG_FILE_DYNAMIC, __version__, db_orm, log_sys_exit, private_cli, setup_logger, tools
+from pyani_plus_b200 import run as run_mod
 from pyani_plus_b200.db_orm import Session
 from pyani_plus_b200.methods import sourmash
 from pyani_plus_b200.utils import available_cores, check_db, check_fasta, fasta_file_stats
@@ -103,6 +104,7 @@ def start_and_run_method(  # noqa: PLR0913, PLR0917
     kmersize: int | None = None,
     minmatch: float | None = None,
     extra: str | None = None,
+    ctx: run_mod.DistContext | None = None,
 ) -> int:
     """Record configuration, genomes and a new run in the database, then compute it."""
     fasta_names = check_fasta(logger, fasta)
@@ -139,7 +141,8 @@ def start_and_run_method(  # noqa: PLR0913, PLR0917
         session.commit()
         msg = f"{method} run setup with {n} genomes in database"
         logger.info(msg)
-        return run_method(logger, executor, cache, temp, workflow_temp, filename_to_md5, database, log, session, run)
+        return run_method(logger, executor, cache, temp, workflow_temp, filename_to_md5, database, log, session, run,
+                          ctx)
 
 
 def run_method(  # noqa: PLR0913, PLR0917
@@ -150,11 +153,22 @@ def run_method(  # noqa: PLR0913, PLR0917
     workflow_temp: Path | None,
     filename_to_md5: dict[Path, str],
     database: Path,
-    log: Path,
+    log: Path,  # noqa: ARG001
     session: Session,
     run: db_orm.Run,
+    ctx: run_mod.DistContext | None = None,
 ) -> int:
-    """Compute the comparisons the run still lacks and record them in the database."""
+    """Compute the comparisons the run still lacks and record them in the database.
+
+    How, depending on what is there (the reference hands all of these to snakemake workers,
+    ``public_cli.py:206-329``):
+
+    * several GPUs (``torchrun``): every rank takes part (``private_cli.compute_sourmash_distributed``);
+    * a fresh small run: the reference's one ``column_0`` job, in-process, through the JSON hand-over;
+    * a fresh large run: the same all-vs-all recorded from arrays;
+    * a partial run (``resume``): only the queries x subjects block that is missing, as one rectangular call.
+    """
+    ctx = ctx or run_mod.DistContext()
     run_id = run.run_id
     method = run.configuration.method
     logger.debug("Counting pre-existing comparisons for this run...")
@@ -172,28 +186,51 @@ def run_method(  # noqa: PLR0913, PLR0917
     if executor != ToolExecutor.local:
         msg = f"Executor {executor.value} is not available: the B200 sourmash engine runs in-process (local)"
         log_sys_exit(logger, msg)
-    # sourmash: all the columns at once, a single worker
-    target = f"{method}.run_{run_id}.column_0.json"
-    logger.debug("Using a single worker")
     run.status = "Running"
     session.commit()
 
-    private_cli.prepare(logger, run, cache)  # builds the .sig cache on the GPU
-
-    if n > BULK_THRESHOLD:
-        logger.debug("Recording comparisons from arrays (bulk path)")
-        private_cli.compute_sourmash_bulk(logger, session, run, cache)
-        done = run.comparisons().count()
-        if done != n**2:
-            msg = f"Only have {done} of {n}²={n**2} {method} comparisons needed"  # pragma: no cover
+    def finish(session_: Session, run_: db_orm.Run) -> int:
+        have = run_.comparisons().count()
+        if have != n**2:
+            msg = f"Only have {have} of {n}²={n**2} {method} comparisons needed"  # pragma: no cover
             log_sys_exit(logger, msg)  # pragma: no cover
-        run.cache_comparisons()
-        run.status = "Done"
-        session.commit()
+        if run_.df_identity is None or done:
+            run_.cache_comparisons()
+        run_.status = "Done"
+        session_.commit()
         msg = f"Completed {method} run-id {run_id} with {n} genomes in database {database}"
         logger.info(msg)
         return 0
 
+    if ctx.world > 1:
+        msg = f"Using {ctx.world} GPUs (one process each)"
+        logger.info(msg)
+        config = run.configuration
+        job = {
+            "entries": sorted((md5, str(path)) for path, md5 in filename_to_md5.items()),
+            "ksize": int(config.kmersize), "scaled": sourmash.parse_scaled(logger, config.extra),
+            "sig_cache": str(cache.absolute() / f"sourmash_k={config.kmersize}_{config.extra}"),
+        }
+        ctx.broadcast_object(job)
+        private_cli.compute_sourmash_distributed(logger, session, job, cache, ctx, run)
+        return finish(session, run)
+
+    private_cli.prepare(logger, run, cache)  # builds the .sig cache on the GPU
+
+    if done:  # resume: one rectangular call for the block that is missing
+        queries, subjects = private_cli.missing_block(run)
+        msg = f"Computing the missing block: {len(queries)} queries x {len(subjects)} subjects"
+        logger.info(msg)
+        private_cli.compute_sourmash_block(logger, session, run, cache, queries, subjects)
+        return finish(session, run)
+    if n > BULK_THRESHOLD:
+        logger.debug("Recording comparisons from arrays (bulk path)")
+        private_cli.compute_sourmash_bulk(logger, session, run, cache)
+        return finish(session, run)
+
+    # sourmash: all the columns at once, a single worker -- the reference's `column_0` job
+    target = f"{method}.run_{run_id}.column_0.json"
+    logger.debug("Using a single worker")
     session.close()  # reduce chance of DB locking
     del run
     with (
@@ -211,19 +248,45 @@ def run_method(  # noqa: PLR0913, PLR0917
             msg = f"compute-column returned {rc} for run-id {run_id}"
             log_sys_exit(logger, msg)
         with db_orm.connect_to_db(logger, database) as session2:
-            run = session2.get_run(run_id)
+            run2 = session2.get_run(run_id)
             if json_path.is_file():
                 private_cli.import_json_comparisons(logger, session2, json_path)
-            done = run.comparisons().count()
-            if done != n**2:
-                msg = f"Only have {done} of {n}²={n**2} {method} comparisons needed"  # pragma: no cover
-                log_sys_exit(logger, msg)  # pragma: no cover
-            run.cache_comparisons()
-            run.status = "Done"
-            session2.commit()
-    msg = f"Completed {method} run-id {run_id} with {n} genomes in database {database}"
-    logger.info(msg)
+            return finish(session2, run2)
+
+
+def _as_worker(logger: logging.Logger, ctx: run_mod.DistContext, cache: Path) -> int:
+    """Ranks other than 0 of a ``torchrun`` launch: no database, no FASTA indexing.  They wait for rank 0 to
+    broadcast the job (or "stop" when there is nothing to compute or rank 0 failed early), take their
+    share of it, and leave."""
+    job = ctx.broadcast_object(None)
+    if job == run_mod.JOB_STOP:
+        return 0
+    private_cli.compute_sourmash_distributed(logger, None, job, cache, ctx)
     return 0
+
+
+class _Rank0Guard:
+    """Makes sure the other ranks are released whatever happens on rank 0 before the job is broadcast."""
+
+    def __init__(self, ctx: run_mod.DistContext) -> None:
+        self.ctx, self.sent = ctx, False
+        if ctx.world > 1:
+            original = ctx.broadcast_object
+
+            def once(obj, src: int = 0):  # noqa: ANN001, ANN202
+                self.sent = True
+                return original(obj, src)
+
+            ctx.broadcast_object = once  # type: ignore[method-assign]
+
+    def __enter__(self) -> "_Rank0Guard":  # noqa: UP037
+        return self
+
+    def __exit__(self, *exc: object) -> None:
+        if self.ctx.world > 1 and not self.sent:
+            self.ctx.broadcast_object(run_mod.JOB_STOP)
+        self.ctx.barrier()
+        self.ctx.close()
 
 
 @app.command("sourmash", rich_help_panel="ANI methods")
@@ -246,11 +309,19 @@ def cli_sourmash(  # noqa: PLR0913
     if log == LOG_FILE_DYNAMIC:
         log = Path("-") if executor == ToolExecutor.local else LOG_FILE
     logger = setup_logger(log, terminal_level=logging.DEBUG if debug else logging.INFO)
-    check_db(logger, database, create_db)
-    return start_and_run_method(
-        logger, executor, cache, temp, wtemp, database, log, name, "sourmash", fasta, tools.get_sourmash(),
-        kmersize=kmersize, extra=f"scaled={scaled}",
-    )
+    ctx = run_mod.DistContext.from_env()  # torchrun: one process per GPU; rank 0 owns the database
+    if ctx.rank != 0:
+        try:
+            return _as_worker(logger, ctx, cache)
+        finally:
+            ctx.barrier()
+            ctx.close()
+    with _Rank0Guard(ctx):
+        check_db(logger, database, create_db)
+        return start_and_run_method(
+            logger, executor, cache, temp, wtemp, database, log, name, "sourmash", fasta, tools.get_sourmash(),
+            kmersize=kmersize, extra=f"scaled={scaled}", ctx=ctx,
+        )
 
 
 @app.command()
@@ -273,6 +344,21 @@ def resume(  # noqa: PLR0913
     if log == LOG_FILE_DYNAMIC:
         log = Path("-") if executor == ToolExecutor.local else LOG_FILE
     logger = setup_logger(log, terminal_level=logging.DEBUG if debug else logging.INFO)
+    ctx = run_mod.DistContext.from_env()
+    if ctx.rank != 0:
+        try:
+            return _as_worker(logger, ctx, cache)
+        finally:
+            ctx.barrier()
+            ctx.close()
+    with _Rank0Guard(ctx):
+        return _resume_rank0(logger, ctx, database, run_id, executor, cache, temp, wtemp, log)
+
+
+def _resume_rank0(  # noqa: PLR0913, PLR0917
+    logger: logging.Logger, ctx: run_mod.DistContext, database: Path, run_id: int | None, executor: ToolExecutor,
+    cache: Path, temp: Path | None, wtemp: Path | None, log: Path,
+) -> int:
     if database == ":memory:" or not Path(database).is_file():
         msg = f"Database {database} does not exist"
         log_sys_exit(logger, msg)
@@ -312,7 +398,7 @@ def resume(  # noqa: PLR0913
                 log_sys_exit(logger, msg)
         run.status = "Resuming"
         session.commit()
-        return run_method(logger, executor, cache, temp, wtemp, filename_to_md5, database, log, session, run)
+        return run_method(logger, executor, cache, temp, wtemp, filename_to_md5, database, log, session, run, ctx)
 
 
 @app.command()

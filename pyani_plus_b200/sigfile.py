@@ -10,11 +10,22 @@ from __future__ import annotations
 
 import hashlib
 import json
+import os
+import struct
 from pathlib import Path
 
 import numpy as np
 
 SEED = 42
+
+# Binary side-cache: ``{md5}.sig.u64`` next to ``{md5}.sig``.  The JSON stays the interchange format (and the
+# only thing other tools read); the side file holds the same hashes as raw little-endian uint64 behind a
+# 48-byte header that ties it to ONE version of the JSON file (its size and mtime), so an externally replaced
+# or edited ``.sig`` silently invalidates it.  Reading 10,000 sketches: ~0.4 GB of binary instead of
+# ~0.9 GB of decimal text through ``json.loads``.
+SIDE_SUFFIX = ".u64"
+_SIDE_MAGIC = b"PANIBSK1"
+_SIDE_HEADER = struct.Struct("<8sIIQQQQ")  # magic, ksize, seed, max_hash, count, sig_size, sig_mtime_ns
 
 
 def sketch_md5sum(hashes: np.ndarray, ksize: int) -> str:
@@ -73,3 +84,43 @@ def read_sig(path: Path, *, ksize: int | None = None) -> dict:
         }
     msg = f"{path} holds no DNA sketch" + (f" with ksize={ksize}" if ksize is not None else "")
     raise ValueError(msg)
+
+
+def side_cache_path(sig_path: Path) -> Path:
+    return sig_path.with_name(sig_path.name + SIDE_SUFFIX)
+
+
+def write_side_cache(sig_path: Path, sig: dict) -> None:
+    """Write the binary twin of ``sig_path`` (best effort: a read-only cache directory is not an error)."""
+    try:
+        st = sig_path.stat()
+        hashes = np.ascontiguousarray(sig["hashes"], dtype="<u8")
+        side = side_cache_path(sig_path)
+        tmp = side.with_name(side.name + f".tmp{os.getpid()}")
+        with tmp.open("wb") as handle:
+            handle.write(_SIDE_HEADER.pack(_SIDE_MAGIC, int(sig["ksize"]), int(sig.get("seed", SEED)),
+                                           int(sig["max_hash"]), int(hashes.size), st.st_size, st.st_mtime_ns))
+            handle.write(hashes.tobytes())
+        tmp.replace(side)
+    except OSError:
+        pass
+
+
+def read_side_cache(sig_path: Path, st: os.stat_result | None = None) -> dict | None:
+    """The sketch from the binary side-cache, or None when it is absent, truncated, or belongs to another
+    version of the ``.sig`` file (size / mtime differ)."""
+    side = side_cache_path(sig_path)
+    try:
+        raw = side.read_bytes()
+    except OSError:
+        return None
+    if len(raw) < _SIDE_HEADER.size:
+        return None
+    magic, ksize, seed, max_hash, count, sig_size, sig_mtime = _SIDE_HEADER.unpack_from(raw)
+    st = st or sig_path.stat()
+    if magic != _SIDE_MAGIC or sig_size != st.st_size or sig_mtime != st.st_mtime_ns or \
+            len(raw) != _SIDE_HEADER.size + 8 * count:
+        return None
+    hashes = np.frombuffer(raw, dtype="<u8", offset=_SIDE_HEADER.size).astype(np.uint64, copy=False)
+    return {"name": sig_path.stem, "filename": "", "ksize": int(ksize), "seed": int(seed), "max_hash": int(max_hash),
+            "md5sum": "", "hashes": hashes}

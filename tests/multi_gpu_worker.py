@@ -33,9 +33,8 @@ bufs = eng.alloc_stream_buffers(plan)
 eng.pack(d_ascii, plan, bufs)
 
 results = {}
-fused = multi_gpu.SymmetricGather.create(per_rank, plan.row_stride, world, rank, eng.device)
+fused = multi_gpu.SymmetricGather.create(per_rank, plan.row_stride, world, rank, eng.device, allow_nccl=True)
 ok = torch.tensor([1 if fused is not None else 0], device=eng.device)
-dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 modes = ["nccl"] + (["fused"] * 2 if int(ok.item()) else [])  # fused twice: the table is re-used
 for mode in modes:
     tab = eng.alloc_table(plan)
@@ -69,6 +68,43 @@ if int(captured.item()):
     results["step_graph"] = (out["table"].to_host(),
                              multi_gpu.combine_partial(out["ov"].clone(), world).cpu().numpy(),
                              int((out["ov"] != 0).sum().item()))
+
+# ---- genomes of very different lengths: every rank plans its own slice, so the row strides differ and the
+# ranks must agree on one before the exchange (run.agree_row_stride); both exchanges, through run.make_step
+from oracle import oracle  # noqa: E402  (test infrastructure: the genomes, and the expected sketches)
+from pyani_plus_b200 import run as run_mod  # noqa: E402
+
+ctx = run_mod.DistContext.from_env()
+N2 = 9
+lengths = [150_000 + 420_000 * g for g in range(N2)]  # rank 0 gets the short ones, the last rank the long ones
+h0, h1, per2 = multi_gpu.slice_for_rank(N2, rank, world)
+mine = [np.frombuffer(oracle.synth_genome(SEED, g, lengths[g]), dtype=np.uint8) for g in range(h0, h1)]
+toff2 = pstream.plan_tiles([len(x) for x in mine] + [0] * (per2 - len(mine)))
+own_stride = eng.plan_stream(toff2, SCALED).row_stride
+plan2 = run_mod.agree_row_stride(eng, toff2, SCALED, ctx)
+strides = [None] * world
+dist.all_gather_object(strides, own_stride)
+h_ascii2 = torch.empty(plan2.n_bases, dtype=torch.uint8)
+pstream.fill_ascii_stream(h_ascii2.numpy(), toff2, [[x] for x in mine] + [[]] * (per2 - len(mine)))
+uneven = {}
+for nccl in (False, True):
+    bufs2 = eng.alloc_stream_buffers(plan2, host_packed=True)
+    tab2 = eng.alloc_table(plan2)
+    step2, exchange2 = run_mod.make_step(eng, plan2, bufs2, tab2, K, ctx, h_ascii=h_ascii2, nccl_gather=nccl)
+    out2 = step2.run(from_host=True)
+    uneven[exchange2] = (out2["table"].to_host(), multi_gpu.combine_partial(out2["ov"].clone(), world).cpu().numpy())
+
+if rank == 0:
+    assert len(set(strides)) > 1, f"test needs ranks whose own strides differ, got {strides}"
+    assert len(uneven) == 2, list(uneven)
+    idx2 = multi_gpu.real_rows(N2, world)
+    want = [oracle.sketch_records([oracle.synth_genome(SEED, g, lengths[g])], K, SCALED) for g in range(N2)]
+    for name, (sk, ov) in uneven.items():
+        for g, r in enumerate(idx2):
+            assert sk[r].tolist() == want[g].tolist(), (name, g)
+        for a, ra in enumerate(idx2):
+            for b, rb in enumerate(idx2):
+                assert ov[ra, rb] == oracle.intersect(want[a], want[b]), (name, a, b)
 
 if rank == 0:
     full, full_off = eng.synth_ascii_stream(SEED, 0, N, LENGTH)

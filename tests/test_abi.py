@@ -139,3 +139,33 @@ def test_ctypes_binding_matches_header(lib: ctypes.CDLL) -> None:
                 assert size == 4, f"{name}: '{decl}' bound as {ctype}"
         checked += 1
     assert checked >= 15
+
+
+def test_pack_host_code_paths_agree(lib: ctypes.CDLL) -> None:
+    """panib_pack_host: scalar, AVX2, AVX-512 and the threaded pool give the words of the device pack
+    (pack.cuh, here through the host emulation library) -- lower case, N runs, non-letters included."""
+    from pyani_plus_b200 import engine
+
+    emu = ctypes.CDLL(str(entry.PKG / "libpanib_hostemu.so"))
+    emu.emu_pack_ascii.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(7)
+    n = 3 * 262144 + 64 * 1021  # several pool blocks plus a ragged tail
+    alphabet = np.frombuffer(b"ACGTacgtNnRY-\n*", dtype=np.uint8)
+    a = rng.choice(alphabet, size=n, p=[.2, .2, .2, .2, .04, .04, .04, .04, .01, .01, .004, .004, .004, .004, .004])
+    a[5000:5040] = ord("N")
+    want_p = np.zeros(n // 16, np.uint32)
+    want_m = np.zeros(n // 32, np.uint32)
+    emu.emu_pack_ascii(a.ctypes.data, n, want_p.ctypes.data, want_m.ctypes.data)
+    ran = 0
+    for threads in (-1, -2, -3, 0, 1, 3):
+        try:
+            got_p, got_m = engine.pack_host(a, threads)
+        except engine.EngineError as exc:  # an instruction set this CPU lacks
+            assert "lacks" in str(exc)
+            continue
+        assert (got_p == want_p).all() and (got_m == want_m).all(), threads
+        ran += 1
+    assert ran >= 4
+    assert lib.panib_host_threads() >= 1
+    with pytest.raises(ValueError, match="multiple of 32"):
+        engine.pack_host(a[:33])

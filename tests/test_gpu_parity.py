@@ -329,10 +329,10 @@ def test_step_pipeline_eager_and_graph(eng) -> None:
     n, length, k, scaled = 12, 400_000, 31, 200
     d_ascii, tile_off = eng.synth_ascii_stream(SEED, 40, n, length)
     plan = eng.plan_stream(tile_off, scaled)
-    bufs = eng.alloc_stream_buffers(plan, ascii_too=True)
+    bufs = eng.alloc_stream_buffers(plan, ascii_too=True, host_packed=True)
     tab = eng.alloc_table(plan)
     eng.pack(d_ascii, plan, bufs)
-    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True)
+    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8)
     h_ascii.copy_(d_ascii)
     want_h, want_c = oracle.synth_sketch_batch(SEED, 40, n, length, k, scaled)
     want_ov = oracle.intersect_all(want_h, want_c)
@@ -348,14 +348,31 @@ def test_step_pipeline_eager_and_graph(eng) -> None:
     out = stepper.run(from_host=True, to_host=True)
     check(out)
     ident_eager = out["identity_host"].clone()
-    for from_host in (False, True):
-        assert stepper.capture(from_host=from_host, to_host=from_host)
-        tab["table"].fill_(7)  # stale rows must be overwritten by the replay
-        for _ in range(2):
-            out = stepper.replay(from_host=from_host, to_host=from_host)
-            stepper.finish()
-        check(out)
+    # the host pack inside the step wrote what the device pack kernel writes
+    assert torch.equal(bufs["h_packed"].to(eng.device), bufs["packed"])
+    assert torch.equal(bufs["h_mask"].to(eng.device), bufs["mask"])
+    assert not stepper.capture(from_host=True, to_host=True)  # host work inside: not a graph
+    assert stepper.capture(to_host=True)
+    tab["table"].fill_(7)  # stale rows must be overwritten by the replay
+    for _ in range(2):
+        out = stepper.replay(to_host=True)
+        stepper.finish()
+    check(out)
     np.testing.assert_array_equal(out["identity_host"].numpy(), ident_eager.numpy())
+    # the older host form (ASCII over PCIe, packed on the device) still gives the same rows
+    eng.sketch_ascii_host(h_ascii.pin_memory(), plan, bufs, tab, k)
+    assert eng.check_status() == 0
+    from pyani_plus_b200 import engine as _eng
+    got = _eng.SketchTable(tab["table"], tab["counts"], k, scaled).to_host()
+    for g in range(n):
+        assert got[g].tolist() == want_h[g, : want_c[g]].tolist(), g
+    # already-packed host buffers (h_ascii = None): copy + K1 only
+    tab["table"].fill_(7)
+    eng.sketch_host(None, plan, bufs, tab, k)
+    assert eng.check_status() == 0
+    got = _eng.SketchTable(tab["table"], tab["counts"], k, scaled).to_host()
+    for g in range(n):
+        assert got[g].tolist() == want_h[g, : want_c[g]].tolist(), g
     ident, _ = engine_ani_host(out["ov"], out["table"], k)
     np.testing.assert_allclose(out["identity_host"].numpy(), ident, rtol=0, atol=ANI_ATOL, equal_nan=True)
     # the inverted-index K2 inside the step, eager and captured (CUB sort + scan inside the graph)

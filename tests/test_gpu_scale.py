@@ -30,5 +30,7 @@ def test_baseline_config_against_oracle(workload: str, sample: int, k2: str) -> 
     assert report["count_cells_with_mismatch"] == 0, report
     assert report["ani_device_vs_host_max_abs_err"] <= 1e-12, report
     assert report["ani_host_rows_not_equal_oracle"] == 0, report
+    # whole-result checksum == the ORACLE's over the complete workload (tests/golden/workload_checksums.json)
+    assert report["oracle_checksum_of_complete_workload"] is not None and report["checksum_ok"], report
     assert report["ok"], report
     assert report["whole_matrix"]["null_pairs"] > 0  # distant descendants share no hash (NULL path)

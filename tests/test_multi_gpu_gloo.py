@@ -99,3 +99,60 @@ def test_two_rank_gloo_pipeline() -> None:
     dummy = sorted(set(range(len(counts))) - set(idx.tolist()))
     assert dummy and (counts[dummy] == 0).all() and (whole[dummy] == 0).all()
     assert 0 < partial_nonzero < int((whole != 0).sum())  # each rank really held only a part
+
+
+def _worker_agreement(rank: int, world: int, port: int, out: dict) -> None:
+    """run.DistContext + the agreement helpers: what ranks with DIFFERENT genome lengths must settle first."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    from pyani_plus_b200 import run as run_mod
+
+    ctx = run_mod.DistContext.from_env()  # gloo here (no CUDA)
+    try:
+        assert (ctx.world, ctx.rank) == (world, rank)
+        # each rank planned its own slice: strides differ (longer genomes on rank 1) -> agree on the maximum
+        my_stride = 1024 * (3 + rank)
+        assert ctx.max_int(my_stride) == 1024 * (2 + world)
+        assert multi_gpu.agree_max(7 - rank, world) == 7
+        # handing rows of different strides to the exchange is refused on EVERY rank, not silently corrupted
+        rows = torch.zeros((4, my_stride), dtype=torch.int64)
+        try:
+            multi_gpu.assert_same_shape(rows)
+            refused = False
+        except ValueError as err:
+            refused = "disagree on the sketch-table shape" in str(err)
+        agreed = torch.zeros((4, ctx.max_int(my_stride)), dtype=torch.int64)
+        multi_gpu.assert_same_shape(agreed)  # no error
+        # the job hand-over of the CLI: rank 0 broadcasts a description (or "stop")
+        job = ctx.broadcast_object({"entries": [("md5", "/x.fna")], "ksize": 31} if rank == 0 else None)
+        stop = ctx.broadcast_object(run_mod.JOB_STOP if rank == 0 else None)
+        ctx.barrier()
+        out[rank] = (refused, job, stop)
+    finally:
+        ctx.close()
+
+
+def test_ranks_agree_on_stride_and_job() -> None:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.get_context("spawn").Manager() as manager:
+        out = manager.dict()
+        mp.spawn(_worker_agreement, args=(2, port, out), nprocs=2, join=True)
+        got = dict(out)
+    for rank in (0, 1):
+        refused, job, stop = got[rank]
+        assert refused
+        assert job == {"entries": [("md5", "/x.fna")], "ksize": 31}
+        assert stop == "stop"
+
+
+def test_single_process_context_is_trivial(monkeypatch: pytest.MonkeyPatch) -> None:
+    from pyani_plus_b200 import run as run_mod
+
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    ctx = run_mod.DistContext.from_env()
+    assert (ctx.world, ctx.rank) == (1, 0)
+    assert ctx.broadcast_object({"a": 1}) == {"a": 1} and ctx.max_int(5) == 5
+    ctx.barrier()
+    ctx.close()

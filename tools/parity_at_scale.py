@@ -120,14 +120,30 @@ def check_workload(workload: str, sample: int = 0, batch: int = 250, k2_method: 
             row_mismatch += 0 if (ident_h[i, j] == row["max_containment_ani"]
                                   and cov_h[i, j] == row["query_containment_ani"]) else 1
 
+    # the COMPLETE result against the oracle's pinned checksum of the complete workload (every hash, every pair)
+    from bench import checksum_weights, expected_checksum  # noqa: PLC0415
+
+    with np.errstate(over="ignore"):
+        ov_ck = np.int64(0)
+        cols = np.arange(n, dtype=np.int64)
+        for r0 in range(0, n, 1024):
+            w = checksum_weights(np.arange(r0, min(n, r0 + 1024), dtype=np.int64), cols)
+            ov_ck = ov_ck + (ov[r0: r0 + 1024] * w).sum(dtype=np.int64)
+    valid = torch.arange(table.rows.shape[1], device=table.rows.device)[None, :] < table.counts[:, None]
+    checksum = {"ov_weighted_sum": int(ov_ck), "hash_sum": int((table.rows * valid).sum().item()),
+                "sketch_total": int(counts.sum())}
+    pinned = expected_checksum(workload)
+    checksum_ok = pinned is None or checksum == pinned
+
     ok = (hash_mismatch == 0 and count_mismatch == 0 and nan_equal and ani_err <= 1e-12 and row_mismatch == 0
-          and props["symmetric"] and props["diag_is_size"] and props["ov_le_min_size"])
+          and props["symmetric"] and props["diag_is_size"] and props["ov_le_min_size"] and checksum_ok)
     return {
         "workload": desc, "n_genomes": n, "genome_bp": length, "k": k, "scaled": scaled, "seed": SEED,
         "checked_genomes": len(ids), "checked_hashes": checked_hashes, "checked_pairs_ordered": int(sub.size),
         "sketches_with_mismatch": hash_mismatch, "count_cells_with_mismatch": count_mismatch,
         "ani_null_pattern_equal": nan_equal, "ani_device_vs_host_max_abs_err": ani_err,
         "ani_host_rows_not_equal_oracle": row_mismatch, "whole_matrix": props,
+        "result_checksum": checksum, "oracle_checksum_of_complete_workload": pinned, "checksum_ok": checksum_ok,
         "sketch_sizes": {"min": int(counts.min()), "mean": float(counts.mean()), "max": int(counts.max())},
         "seconds": {"gpu_generate_sketch_intersect": gpu_s, "oracle_sketch": sketch_s, "oracle_intersect": inter_s},
         "k2_method": k2_used, "oracle_threads": oracle.num_threads(), "library": engine.library_version(), "ok": ok}
