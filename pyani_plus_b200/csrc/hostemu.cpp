@@ -49,7 +49,7 @@ static int64_t run(const uint32_t *packed, const uint32_t *mask, int64_t t0, int
     constexpr int S = kTileBases / kCtaTile;  // CTA tiles per stream tile
     static uint32_t stage[kSpLead + kTileWords];          // the kernel's staged tile with its lead-in words
     static uint32_t rcp_[kSpLead + kTileWords];           // packed reverse stream (phase A -> phase B)
-    static uint32_t scratch[2 * kBlkWords * kThreadsK1];  // all threads' scratch blocks (shared memory on the GPU)
+    static uint32_t scratch[2 * kBlkPos * kThreadsK1];  // all threads' scratch blocks (shared memory on the GPU)
     for (int64_t tile = t0 * S; tile < t1 * S; tile++) {
         const uint32_t *sm = mask + tile * (kCtaTile / 32);
         for (int i = 0; i < kSpLead; i++) stage[i] = 0xDEADBEEFu;  // content must not matter
@@ -65,7 +65,7 @@ static int64_t run(const uint32_t *packed, const uint32_t *mask, int64_t t0, int
         for (int tid = 0; tid < kThreadsK1; tid++) {
             const int u = tid >> 2, a = tid & 3;
             const uint32_t vmask = any ? thread_valid_mask<K>(sm, u, a) : 0xFFFFu;
-            hash_thread_kmers<K>(sp, rcp, scratch + tid, kThreadsK1, u, a, vmask, hc, c);
+            hash_thread_kmers<K>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, c);
         }
     }
     return c.n;

@@ -93,17 +93,24 @@ index_insert_kernel(const uint64_t *__restrict__ rows, const int32_t *__restrict
 }
 
 // step 2: one thread per entry; the group's first arrival classifies the group.
-// stats: [0] columns, [1] pairs the rare groups expand to, [2] distinct hashes, [3] list words handed out
+// stats: [0] columns, [1] pairs the rare groups expand to, [2] distinct hashes, [3] list words handed out.
+// Columns and list space are handed out per CTA round (warp scans, then one scan over the 8 warp totals and
+// ONE atomic per counter), the two pure statistics once per CTA: a single address takes an atomic every
+// nanosecond or two, and there are millions of entries.
 __global__ void __launch_bounds__(kIdxThreads)
 index_classify_kernel(const int32_t *__restrict__ counts, int n, int cap, const int64_t *__restrict__ offsets,
                       int64_t total, int tau, const uint32_t *__restrict__ tcount, uint32_t *__restrict__ taux,
                       const uint32_t *__restrict__ eslot, const uint32_t *__restrict__ eidx,
                       unsigned long long *__restrict__ stats) {
-    const unsigned lane = threadIdx.x & 31;
+    constexpr int kWarps = kIdxThreads / 32;
+    __shared__ uint32_t s_freq[kWarps], s_rare[kWarps];
+    __shared__ unsigned long long s_cbase, s_lbase;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long pairs = 0ull, distinct = 0ull;  // per thread, reduced once at the end
     for (int g = blockIdx.x; g < n; g += gridDim.x) {
         const int c = offsets ? counts[g] : min(counts[g], cap);
         const int rounds = (c + (int)(gridDim.y * kIdxThreads) - 1) / (int)(gridDim.y * kIdxThreads);
-        for (int r = 0; r < rounds; r++) {  // whole warps stay in the loop: the ballots below need them
+        for (int r = 0; r < rounds; r++) {  // whole CTAs stay in the loop: the barriers below need them
             const int i = (r * gridDim.y + blockIdx.y) * kIdxThreads + threadIdx.x;
             uint32_t slot = kNoSlot, m = 0;
             if (i < c) {
@@ -112,40 +119,48 @@ index_classify_kernel(const int32_t *__restrict__ counts, int n, int cap, const 
                 if (slot != kNoSlot) m = tcount[slot];
             }
             const bool frequent = m >= (uint32_t)tau, rare = m >= 2 && !frequent;
-            // columns: one atomic per warp
             const unsigned fmask = __ballot_sync(0xFFFFFFFFu, frequent);
-            unsigned long long cbase = 0;
-            if (fmask) {
-                if (lane == (unsigned)(__ffs(fmask) - 1)) cbase = atomicAdd(stats + 0, (unsigned long long)__popc(fmask));
-                cbase = __shfl_sync(0xFFFFFFFFu, cbase, __ffs(fmask) - 1);
-            }
-            // list space: warp-wide exclusive scan of the rare group sizes, one atomic per warp
-            uint32_t incl = rare ? m : 0u;
+            uint32_t incl = rare ? m : 0u;  // warp-wide inclusive scan of the rare group sizes
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                 if (lane >= (unsigned)o) incl += v;
             }
-            const uint32_t wsum = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            unsigned long long lbase = 0;
-            if (wsum) {
-                if (lane == 31) lbase = atomicAdd(stats + 3, (unsigned long long)wsum);
-                lbase = __shfl_sync(0xFFFFFFFFu, lbase, 31);
+            if (lane == 31) {
+                s_freq[warp] = (uint32_t)__popc(fmask);
+                s_rare[warp] = incl;
             }
-            if (frequent) taux[slot] = kFrequent | (uint32_t)(cbase + __popc(fmask & ((1u << lane) - 1u)));
-            else if (rare) taux[slot] = (uint32_t)(lbase + incl - m);
-            unsigned long long pairs = rare ? (unsigned long long)m * (m - 1) / 2ull : 0ull;
-            unsigned long long distinct = slot != kNoSlot ? 1ull : 0ull;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t f = 0, w = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
-                distinct += __shfl_xor_sync(0xFFFFFFFFu, distinct, o);
+                for (int k = 0; k < kWarps; k++) {  // exclusive scan of the warp totals, in place
+                    const uint32_t fk = s_freq[k], wk = s_rare[k];
+                    s_freq[k] = f;
+                    s_rare[k] = w;
+                    f += fk;
+                    w += wk;
+                }
+                s_cbase = f ? atomicAdd(stats + 0, (unsigned long long)f) : 0ull;
+                s_lbase = w ? atomicAdd(stats + 3, (unsigned long long)w) : 0ull;
             }
-            if (lane == 0) {
-                if (pairs) atomicAdd(stats + 1, pairs);
-                if (distinct) atomicAdd(stats + 2, distinct);
-            }
+            __syncthreads();
+            if (frequent)
+                taux[slot] = kFrequent | (uint32_t)(s_cbase + s_freq[warp] + __popc(fmask & ((1u << lane) - 1u)));
+            else if (rare) taux[slot] = (uint32_t)(s_lbase + s_rare[warp] + incl - m);
+            if (rare) pairs += (unsigned long long)m * (m - 1) / 2ull;
+            if (slot != kNoSlot) distinct += 1ull;
+            __syncthreads();  // s_* are rewritten in the next round
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+        distinct += __shfl_xor_sync(0xFFFFFFFFu, distinct, o);
+    }
+    if (lane == 0) {
+        if (pairs) atomicAdd(stats + 1, pairs);
+        if (distinct) atomicAdd(stats + 2, distinct);
     }
 }
 
@@ -384,7 +399,11 @@ extern "C" int panib_index_build(const uint64_t *d_rows, const int32_t *d_counts
                                                       max_hash, sh, tkeys, tcount, eslot, eidx, d_status);
     rc = check_launch("index_insert_kernel");
     if (rc) return rc;
-    index_classify_kernel<<<grid, kIdxThreads, 0, st>>>(d_counts, (int)n, (int)cap, d_offsets, L.total, tau, tcount,
+    // fewer, looping CTAs here: the kernel ends with two statistics atomics per warp
+    dim3 cgrid = grid;
+    if (cgrid.x > 296) cgrid.x = 296;
+    if (cgrid.y > 8) cgrid.y = 8;
+    index_classify_kernel<<<cgrid, kIdxThreads, 0, st>>>(d_counts, (int)n, (int)cap, d_offsets, L.total, tau, tcount,
                                                         taux, eslot, eidx,
                                                         reinterpret_cast<unsigned long long *>(d_stats));
     return check_launch("index_classify_kernel");

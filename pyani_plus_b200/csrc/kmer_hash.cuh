@@ -20,6 +20,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define PANIB_HD __host__ __device__ __forceinline__
 #else
@@ -282,7 +284,7 @@ struct Geom {
     // 4 * (kCtaTile/4 - 1 - 16u - j) + (3 - a): word-aligned in the copy shifted by 3 - a bytes, and
     // 4-byte steps apart for consecutive j, exactly like the forward strand.  Packed word v of RCm is the
     // reverse complement of the 16 tile bases starting at 16 * (NI - v) + K - 17.
-    static constexpr int RC_D = K - 21;  // first base of the 20-base group of item v: 16 * (NI - v) + RC_D
+    static constexpr int RC_D = K - 17;  // first base of the 16-base window of item v: 16 * (NI - v) + RC_D
     static constexpr int RC_DQ = RC_D >= 0 ? RC_D / 16 : -((15 - RC_D) / 16);  // floor(RC_D / 16)
     static constexpr int RC_DR = RC_D - 16 * RC_DQ;                            // 0..15
 };
@@ -343,47 +345,76 @@ PANIB_HD uint64_t window(const uint32_t *X, int off) {
 //
 // Phase B (hash_thread_kmers): thread (u, a) hashes its 16 k-mers.  Its scratch block holds the ASCII
 // words of its span for both strands, so k-mer j reads its NWD words from
-// `fwd ? blk + j : blk + kBlkWords + 15 - j`: the canonical choice costs one address select and the
+// forward or its reverse block (one address select; see the layout below): the canonical choice costs one select and the
 // words arrive through the otherwise idle load/store pipe.
 //
-// Scratch layout (kBlkWords words per strand and thread, element-major): element e of thread tid lives
-// at scratch[e * nthreads + tid] (forward) / scratch[(kBlkWords + e) * nthreads + tid] (reverse): a
-// warp's accesses to one element are 32 consecutive words whatever strand each lane picks.
-//   forward element e of thread (u, a) = tile bytes   [64u + a + 4e, +4)  = word 16u + e of the copy shifted by a
-//   reverse element e of thread (u, a) = RCm bytes [64(NU-1-u) + (3-a) + 4e, +4) = word 16(NU-1-u) + e of the
-//                                        copy shifted by 3 - a
-// so word w of a shifted copy goes to block w >> 4 at element w & 15 and, because spans overlap by
-// NA - 16 words, also to the neighbouring block at element (w & 15) + 16 when that is < NA.
+// Scratch layout: per strand and thread kBlkPos = 24 word positions, stored as 12 PAIRS; pair r of thread
+// tid lives at scratch[((strand * 12 + r) * nthreads + tid) * 2 .. +2).  A warp's 64-bit access to one pair
+// is 256 consecutive bytes whatever strand each lane picks (two wavefronts, the minimum), phase A stores
+// pairs with one STS.64 and phase B loads a k-mer's 8 words with 4 (even j) or 5 (odd j) loads instead of 8.
+//   forward position p of thread (u, a) = tile bytes [64u + a + 4p, +4)       = word 16u + p of the copy shifted by a
+//   reverse position p of thread (u, a) = RCm bytes [64(NU-1-u) + (3-a) + 4(p-1), +4)
+//                                       = word 16(NU-1-u) + p of the copy shifted by 3 - a of the stream
+//                                         RCn = RCm delayed by one word (4 bases)
+// The one-word delay makes k-mer j start at position j on the forward and 16 - j on the reverse strand: the
+// same parity, so both strands of a k-mer are loaded with the same instruction shapes.  Word w of a shifted
+// copy goes to block w >> 4 at position w & 15 and, because spans overlap, also to the neighbouring block
+// at position (w & 15) + 16 when w & 15 < 8.  (Reverse position 0 and forward position 23 are never read.)
 // ================================================================================================
-constexpr int kBlkWords = 23;  // ASCII words per strand of a span: ceil((60 + 32) / 4)
+constexpr int kBlkPos = 24;    // word positions per strand of a span (ceil((60 + 32) / 4) = 23 used, + the delay)
+constexpr int kBlkPairs = kBlkPos / 2;
 constexpr int kSpLead = 4;     // readable words in front of the staged packed tile (content irrelevant)
 
+// index of word position p of `strand` in thread tid's scratch
+PANIB_HD int scr_index(int strand, int p, int tid, int nthreads) {
+    return ((strand * kBlkPairs + (p >> 1)) * nthreads + tid) * 2 + (p & 1);
+}
+PANIB_HD void load_pair(const uint32_t *at, uint32_t &v0, uint32_t &v1) {
+#if defined(__CUDA_ARCH__)
+    const uint2 v = *reinterpret_cast<const uint2 *>(at);
+    v0 = v.x;
+    v1 = v.y;
+#else
+    v0 = at[0];
+    v1 = at[1];
+#endif
+}
+PANIB_HD void store_pair(uint32_t *at, uint32_t v0, uint32_t v1) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint2 *>(at) = make_uint2(v0, v1);
+#else
+    at[0] = v0;
+    at[1] = v1;
+#endif
+}
+
 // packed word v of the reverse stream RCm (reverse complement of the 16 tile bases from 16(NI - v) + K - 17)
-// and, in g8, the 4 tile bases in front of them (they become the first 4 bases of word v + 1)
+// and, in g8, the 4 tile bases BEHIND them (their reverse complement is the last 4 bases of word v - 1)
 template <int K>
 PANIB_HD uint32_t rc_packed_word(const uint32_t *sp, int v, uint32_t &g8) {
     using G_ = Geom<K>;
     const uint32_t *s = sp + (G_::NI - v + G_::RC_DQ);
-    constexpr int sh = 2 * G_::RC_DR;
+    constexpr int sh = 2 * G_::RC_DR;  // bit offset of the 16-base window in s[0]
     uint32_t g32;
-    if constexpr (sh == 0) g8 = s[0] & 0xFFu;
-    else g8 = shf_r(s[0], s[1], sh) & 0xFFu;
-    if constexpr (sh + 8 < 32) g32 = shf_r(s[0], s[1], sh + 8);
-    else if constexpr (sh + 8 == 32) g32 = s[1];
-    else g32 = shf_r(s[1], s[2], sh + 8 - 32);
+    if constexpr (sh == 0) {
+        g32 = s[0];
+        g8 = s[1] & 0xFFu;
+    } else {
+        g32 = shf_r(s[0], s[1], sh);
+        if constexpr (sh + 8 <= 32) g8 = (s[1] >> sh) & 0xFFu;
+        else g8 = shf_r(s[1], s[2], sh) & 0xFFu;
+    }
     return revcomp16(g32);
 }
 
-// Phase A for item t (0 <= t < Geom<K>::NI; the halo items are tile_expand_halo's).  sp[-1] .. sp[NI + 2] must be readable; rcp receives
-// packed word t of the reverse stream (used by phase B for the canonical comparison).
-// In round r the lane stores the copy shifted by (t + r) & 3 bytes: the four lanes that share a block
-// then write four different threads' slots, which makes every store instruction of a warp hit 32
-// different banks.
+// Phase A for item t (0 <= t < Geom<K>::NI; the halo items are tile_expand_halo's).  sp[-1] .. sp[NI + 2] must
+// be readable; rcp receives packed word t of the reverse stream (phase B compares on it).
+// In round r the lane stores the copy shifted by (t + r) & 3 bytes: the four lanes that share a block then
+// write four different threads' slots, which keeps a warp's store on 32 different 8-byte columns.
 template <int K>
 PANIB_HD void tile_expand_item(const uint32_t *sp, uint32_t *rcp, uint32_t *scratch, int nthreads, int t) {
     using G_ = Geom<K>;
-    constexpr int NA = G_::NA;
-    static_assert(NA <= kBlkWords && NA - 16 <= 7, "scratch block too small");
+    static_assert(G_::NA <= kBlkPos - 1, "scratch block too small");
     const int up = t >> 2, m = t & 3;
     uint32_t sel[4];
     int ar[4];
@@ -392,78 +423,77 @@ PANIB_HD void tile_expand_item(const uint32_t *sp, uint32_t *rcp, uint32_t *scra
         ar[r] = (m + r) & 3;
         sel[r] = 0x3210u + 0x1111u * (uint32_t)ar[r];
     }
-    const bool nb_ok = up >= 1;
+    const bool sec = up >= 1 && m < 2;  // positions 4m .. 4m+3 also feed the neighbouring block at +16
     uint32_t E[5];
-    // ---- forward strand: tile bases [16t, 16t + 20)
+    // ---- forward strand: tile bases [16t, 16t + 20) -> words 4t .. 4t+3 of the four shifted copies
     expand16(sp[t], E);
     E[4] = expand4(sp[t + 1] & 0xFFu);
     {
-        uint32_t *p0 = scratch + (4 * m) * nthreads + 4 * up;
+        uint32_t *p0 = scratch + scr_index(0, 4 * m, 4 * up, nthreads);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const bool sec = nb_ok && (4 * m + i + 16 < NA);
+        for (int h = 0; h < 2; h++) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const uint32_t v = prmt(E[i], E[i + 1], sel[r]);
-                uint32_t *p = p0 + i * nthreads + ar[r];
-                p[0] = v;
-                if (sec) p[16 * nthreads - 4] = v;
+                const uint32_t v0 = prmt(E[2 * h], E[2 * h + 1], sel[r]);
+                const uint32_t v1 = prmt(E[2 * h + 1], E[2 * h + 2], sel[r]);
+                uint32_t *p = p0 + h * (2 * nthreads) + 2 * ar[r];
+                store_pair(p, v0, v1);
+                if (sec) store_pair(p + 8 * (2 * nthreads) - 8, v0, v1);
             }
         }
     }
-    // ---- reverse strand: RCm positions [16t, 16t + 20) = reverse complement of tile bases
-    //      [16(NI - t) + RC_D, +20), of which the last 16 make packed word t of RCm
+    // ---- reverse strand: words 4t .. 4t+3 of the copies of RCn = RCm words 4t-1 .. 4t+2: the last word of
+    //      RCm packed word t-1 (reverse complement of the 4 bases behind the window) and packed word t itself
     {
         uint32_t g8;
         const uint32_t rcw = rc_packed_word<K>(sp, t, g8);
         rcp[t] = rcw;
-        expand16(rcw, E);
-        E[4] = expand4(revcomp16(g8 << 24) & 0xFFu);
-        uint32_t *p0 = scratch + (kBlkWords + 4 * m) * nthreads + 4 * (G_::NU - 1 - up) + 3;
+        E[0] = expand4(revcomp16(g8 << 24) & 0xFFu);
+        expand16(rcw, E + 1);
+        uint32_t *p0 = scratch + scr_index(1, 4 * m, 4 * (G_::NU - 1 - up) + 3, nthreads);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const bool sec = nb_ok && (4 * m + i + 16 < NA);
+        for (int h = 0; h < 2; h++) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const uint32_t v = prmt(E[i], E[i + 1], sel[r]);
-                uint32_t *p = p0 + i * nthreads - ar[r];
-                p[0] = v;
-                if (sec) p[16 * nthreads + 4] = v;
+                const uint32_t v0 = prmt(E[2 * h], E[2 * h + 1], sel[r]);
+                const uint32_t v1 = prmt(E[2 * h + 1], E[2 * h + 2], sel[r]);
+                uint32_t *p = p0 + h * (2 * nthreads) - 2 * ar[r];
+                store_pair(p, v0, v1);
+                if (sec) store_pair(p + 8 * (2 * nthreads) + 8, v0, v1);
             }
         }
     }
 }
 
-// Phase A, halo: the K-1 bases behind the tile (items NI, NI+1) only feed the overlap elements 16..NA-1 of
-// the last forward block (u = NU-1) and of the last reverse block (u = 0).  ONE warp does this, one
-// (strand, word, pair of shifts) per lane, so that no warp is a whole item behind the others at the
-// barrier.  Lanes 14 / 15 (idle otherwise) store the two packed reverse words the last block compares.
+// Phase A, halo: the K-1 bases behind the tile only feed positions 16.. of the last forward block (u = NU-1)
+// and of the last reverse block (u = 0).  ONE warp does this, one (strand, word, pair of shifts) per lane, so
+// that no warp is a whole item behind the others at the barrier.  The forward lanes of word 7 (position 23,
+// never read) store the two packed reverse words the last block compares instead.
 template <int K>
 PANIB_HD void tile_expand_halo(const uint32_t *sp, uint32_t *rcp, uint32_t *scratch, int nthreads, int lane) {
     using G_ = Geom<K>;
-    constexpr int NA = G_::NA;
     const int strand = lane >> 4, hw = (lane >> 1) & 7, ap = lane & 1;
-    if (hw < NA - 16) {
-        uint32_t g16;
-        if (strand == 0) {  // tile bases [kCtaTile + 4hw, +8)
-            const uint32_t *s = sp + G_::NI + (hw >> 2);
-            g16 = shf_r(s[0], s[1], 8u * (uint32_t)(hw & 3)) & 0xFFFFu;
-        } else {  // RCm positions [kCtaTile + 4hw, +8) = reverse complement of tile bases [K - 9 - 4hw, +8)
-            const int tb = K - 9 - 4 * hw;
-            const uint32_t *s = sp + (tb >> 4);  // arithmetic shift: the lead-in words cover tb < 0
-            g16 = revcomp16(shf_r(s[0], s[1], 2u * (uint32_t)(tb & 15)) << 16) & 0xFFFFu;
-        }
-        const uint32_t e0 = expand4(g16 & 0xFFu), e1 = expand4(g16 >> 8);
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int sft = 2 * ap + q;  // copy shifted by sft bytes
-            const uint32_t v = prmt(e0, e1, 0x3210u + 0x1111u * (uint32_t)sft);
-            if (strand == 0) scratch[(16 + hw) * nthreads + 4 * (G_::NU - 1) + sft] = v;
-            else scratch[(kBlkWords + 16 + hw) * nthreads + 3 - sft] = v;
-        }
-    } else if (strand == 0) {
+    if (strand == 0 && hw == 7) {
         uint32_t g8;
         rcp[G_::NI + ap] = rc_packed_word<K>(sp, G_::NI + ap, g8);
+        return;
+    }
+    uint32_t g16;
+    if (strand == 0) {  // forward word 4NI + hw: tile bases [kCtaTile + 4hw, +8)
+        const uint32_t *s = sp + G_::NI + (hw >> 2);
+        g16 = shf_r(s[0], s[1], 8u * (uint32_t)(hw & 3)) & 0xFFFFu;
+    } else {  // RCn word 4NI + hw = RCm bases [kCtaTile - 4 + 4hw, +8) = reverse complement of tile bases [K-5-4hw, +8)
+        const int tb = K - 5 - 4 * hw;
+        const uint32_t *s = sp + (tb >> 4);  // arithmetic shift: the lead-in words cover tb < 0
+        g16 = revcomp16(shf_r(s[0], s[1], 2u * (uint32_t)(tb & 15)) << 16) & 0xFFFFu;
+    }
+    const uint32_t e0 = expand4(g16 & 0xFFu), e1 = expand4(g16 >> 8);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int sft = 2 * ap + q;  // copy shifted by sft bytes
+        const uint32_t v = prmt(e0, e1, 0x3210u + 0x1111u * (uint32_t)sft);
+        if (strand == 0) scratch[scr_index(0, 16 + hw, 4 * (G_::NU - 1) + sft, nthreads)] = v;
+        else scratch[scr_index(1, 16 + hw, 3 - sft, nthreads)] = v;
     }
 }
 
@@ -482,6 +512,37 @@ PANIB_HD uint32_t thread_valid_mask(const uint32_t *sm, int u, int a) {
     return vm;
 }
 
+// ---- phase B loads: the thread's scratch through a 32-bit shared-memory address and explicit ld.shared with
+// compile-time offsets (left to itself nvcc re-derives the shared window base for every k-mer); plain
+// pointers in the host emulation
+#if defined(__CUDA_ARCH__)
+using ScrBase = uint32_t;
+PANIB_HD ScrBase scr_base(const uint32_t *blk) { return (uint32_t)__cvta_generic_to_shared(blk); }
+PANIB_HD ScrBase scr_advance(ScrBase b, int bytes) { return b + (uint32_t)bytes; }
+template <int OFF>
+PANIB_HD void scr_load2(ScrBase b, uint32_t &v0, uint32_t &v1) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v0), "=r"(v1) : "r"(b), "n"(OFF));
+}
+template <int OFF>
+PANIB_HD uint32_t scr_load1(ScrBase b) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(b), "n"(OFF));
+    return v;
+}
+#else
+using ScrBase = const uint8_t *;
+PANIB_HD ScrBase scr_base(const uint32_t *blk) { return reinterpret_cast<const uint8_t *>(blk); }
+PANIB_HD ScrBase scr_advance(ScrBase b, int bytes) { return b + bytes; }
+template <int OFF>
+PANIB_HD void scr_load2(ScrBase b, uint32_t &v0, uint32_t &v1) {
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(b + OFF);
+    v0 = p[0];
+    v1 = p[1];
+}
+template <int OFF>
+PANIB_HD uint32_t scr_load1(ScrBase b) { return *reinterpret_cast<const uint32_t *>(b + OFF); }
+#endif
+
 // 64 bits of a packed multiword value starting at (compile-time) bit offset `off`, no masking
 template <int NXW>
 PANIB_HD void window64(const uint32_t *X, int off, uint32_t &lo, uint32_t &hi) {
@@ -495,10 +556,64 @@ PANIB_HD void window64(const uint32_t *X, int off, uint32_t &lo, uint32_t &hi) {
     }
 }
 
+// k-mer J of a thread (compile-time J: every scratch offset is an immediate); recursion = the unrolled loop
+template <int K, int J, class Emit>
+struct KmerStep {
+    using G_ = Geom<K>;
+    static constexpr int NX = G_::NX, NWD = G_::NWD;
+    static constexpr bool WHOLE = (K == 31 || K == 32);
+    static constexpr int ROW = 2 * kThreadsK1 * 4;  // bytes between pair rows
+
+    template <int Q>
+    static PANIB_HD void pairs_even(ScrBase b, uint32_t *W) {
+        if constexpr (Q < (NWD + 1) / 2) {
+            scr_load2<((J >> 1) + Q) * ROW>(b, W[2 * Q], W[2 * Q + 1]);
+            pairs_even<Q + 1>(b, W);
+        }
+    }
+    template <int Q>
+    static PANIB_HD void pairs_odd(ScrBase b, uint32_t *W) {
+        if constexpr (Q < NWD / 2) {
+            scr_load2<((J >> 1) + 1 + Q) * ROW>(b, W[2 * Q + 1], W[2 * Q + 2]);
+            pairs_odd<Q + 1>(b, W);
+        }
+    }
+
+    static PANIB_HD void run(const uint32_t *X, const uint32_t *Xr, ScrBase fw, uint32_t vmask,
+                             const HashConsts &hc, Emit &emit) {
+        if constexpr (J < kKmersPerThread) {
+            bool lt;
+            if constexpr (WHOLE) {
+                uint32_t flo, fhi, rlo, rhi;
+                window64<NX>(X, 8 * J, flo, fhi);
+                window64<NX>(Xr, 8 * (kKmersPerThread - 1 - J), rlo, rhi);
+                lt = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
+            } else {
+                lt = window<K, NX>(X, 8 * J) < window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - J));
+            }
+            // forward words at positions J + i, reverse words at 16 - J + i (same parity): the same pair rows
+            // of the forward block, or kBlkPairs + 8 - J rows further in the reverse block: one select, one add
+            const ScrBase b = scr_advance(fw, lt ? 0 : (kBlkPairs + 8 - J) * ROW);
+            uint32_t W[NWD + 1];
+            if constexpr ((J & 1) == 0) {
+                pairs_even<0>(b, W);
+            } else {  // one word, then pairs (the last pair may bring one word too many)
+                W[0] = scr_load1<(J >> 1) * ROW + 4>(b);
+                pairs_odd<0>(b, W);
+            }
+            const Partial p = murmur_words<K>(W, hc);
+            if (p.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
+                if (vmask & (1u << J)) emit(p);
+            }
+            KmerStep<K, J + 1, Emit>::run(X, Xr, fw, vmask, hc, emit);
+        }
+    }
+};
+
 // Phase B: hash the 16 k-mers of thread (u, a) of a tile.
 //   sp    : packed words of the tile (word 0 bit 0 = tile position 0); sp[-1] readable
 //   rcp   : packed words of the reverse stream RCm (written by phase A); rcp[-1] readable
-//   blk   : this thread's scratch (scratch + tid), stride blk_stride between elements
+//   blk   : this thread's scratch (scratch + 2 * tid; the CTA's scratch has kThreadsK1 threads per pair row)
 //   vmask : bit j set = k-mer j is valid (0xFFFF for a tile without invalid bases)
 //   emit  : callable(const Partial &) invoked for every valid k-mer that passes the prefilter
 //
@@ -509,10 +624,10 @@ PANIB_HD void window64(const uint32_t *X, int off, uint32_t &lo, uint32_t &hi) {
 // real bases tie -- impossible, an odd-length k-mer is never its own reverse complement.  Windows of
 // every fourth k-mer are register-aligned.  Other K use masked windows.
 template <int K, class Emit>
-PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *rcp, const uint32_t *blk, int blk_stride,
-                                int u, int a, uint32_t vmask, const HashConsts &hc, Emit &&emit) {
+PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *rcp, const uint32_t *blk, int u, int a,
+                                uint32_t vmask, const HashConsts &hc, Emit &&emit) {
     using G_ = Geom<K>;
-    constexpr int NX = G_::NX, NWD = G_::NWD;
+    constexpr int NX = G_::NX;
     constexpr bool WHOLE = (K == 31 || K == 32);  // 64-bit windows without masks
     constexpr int EARLY = WHOLE ? 32 - K : 0;     // bases the spans start early
     uint32_t X[NX], Xr[NX];
@@ -530,30 +645,7 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *rcp, const u
             Xr[w] = shf_r(srcr[w], srcr[w + 1], sr);
         }
     }
-    const uint32_t *fw = blk;
-    constexpr int RV0 = kBlkWords + kKmersPerThread - 1;  // reverse element of k-mer j: RV0 - j (+ i)
-#pragma unroll
-    for (int j = 0; j < kKmersPerThread; j++) {
-        bool lt;
-        if constexpr (WHOLE) {
-            uint32_t flo, fhi, rlo, rhi;
-            window64<NX>(X, 8 * j, flo, fhi);
-            window64<NX>(Xr, 8 * (kKmersPerThread - 1 - j), rlo, rhi);
-            lt = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
-        } else {
-            lt = window<K, NX>(X, 8 * j) < window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - j));
-        }
-        // forward words at element j + i, reverse words at RV0 - j + i: one select, one add
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(
-            reinterpret_cast<const char *>(fw) + (lt ? 0 : (RV0 - 2 * j) * blk_stride * 4));
-        uint32_t W[NWD];
-#pragma unroll
-        for (int i = 0; i < NWD; i++) W[i] = words[(j + i) * blk_stride];
-        const Partial p = murmur_words<K>(W, hc);
-        if (p.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
-            if (vmask & (1u << j)) emit(p);
-        }
-    }
+    KmerStep<K, 0, typename std::remove_reference<Emit>::type>::run(X, Xr, scr_base(blk), vmask, hc, emit);
 }
 
 }  // namespace panib

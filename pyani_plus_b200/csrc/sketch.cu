@@ -144,8 +144,8 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     __shared__ __align__(16) uint32_t rcp_[kSpStage];
     __shared__ GenomeSlot s_slot;
     __shared__ int64_t s_next;
-    // per-thread ASCII scratch, element-major: element e of thread t at scratch[e * kThreadsK1 + t]
-    extern __shared__ uint32_t scratch[];  // kK1DynSmem bytes
+    // per-thread ASCII scratch as pairs of words (kmer_hash.cuh: scr_index)
+    extern __shared__ __align__(16) uint32_t scratch[];  // kK1DynSmem bytes
     constexpr int S = kTileBases / kCtaTile;
     n_tiles *= S;
     int64_t tile = tile_begin * S + blockIdx.x;
@@ -196,7 +196,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         const bool dirty = __syncthreads_or(mw != 0u) != 0;
         // phase B
         const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
-        hash_thread_kmers<K>(sp, rcp, scratch + tid, kThreadsK1, u, a, vmask, hc, emit);
+        hash_thread_kmers<K>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, emit);
         tile = next;
         next = s_next;  // written before the barrier above, overwritten after the next one
     }
@@ -422,7 +422,7 @@ static dim3 tile_grid(int64_t n_tiles) {  // one CTA per tile (generic kernel); 
     return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
-constexpr size_t kK1DynSmem = 2 * kBlkWords * kThreadsK1 * sizeof(uint32_t);  // per-thread ASCII scratch
+constexpr size_t kK1DynSmem = 2 * kBlkPos * kThreadsK1 * sizeof(uint32_t);  // per-thread ASCII scratch
 
 // persistent grid of the fast kernel: SMs x resident CTAs per SM
 template <int K>
