@@ -113,6 +113,13 @@ PANIB_API int panib_sketch_stream(const uint32_t *d_packed, const uint32_t *d_ma
                         int64_t row_stride, int32_t *d_counts, int32_t *d_flags, int32_t *d_status,
                         void *stream);
 
+/* Optional scratch for the sketch calls of the CURRENT device (d_ptr stays owned by the caller and must outlive
+ * them; NULL / 0 unregisters; sketch calls of one device that use it must not run concurrently).  With it K1
+ * parks the surviving hashes per CTA and a second kernel inserts them into the table rows afterwards, instead
+ * of inserting one by one from the hashing loop; results are identical.  2 * 12 bytes per expected survivor
+ * (bases / scaled) of the largest single call, plus a few KB, is plenty; a smaller one is simply not used. */
+PANIB_API int panib_set_workspace(void *d_ptr, int64_t bytes);
+
 /* The two halves of panib_sketch_stream, exposed for profiling / benchmarking. */
 PANIB_API int panib_sketch_hash_only(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
                            int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,

@@ -556,6 +556,9 @@ PANIB_HD void window64(const uint32_t *X, int off, uint32_t &lo, uint32_t &hi) {
     }
 }
 
+#ifndef PANIB_K1_GROUP
+#define PANIB_K1_GROUP 1
+#endif
 // k-mer J of a thread (compile-time J: every scratch offset is an immediate); recursion = the unrolled loop
 template <int K, int J, class Emit>
 struct KmerStep {
@@ -579,33 +582,48 @@ struct KmerStep {
         }
     }
 
+    // canonical choice + loads + hash of k-mer J (no side effects: callers can interleave several)
+    static PANIB_HD Partial hash_one(const uint32_t *X, const uint32_t *Xr, ScrBase fw, const HashConsts &hc) {
+        bool lt;
+        if constexpr (WHOLE) {
+            uint32_t flo, fhi, rlo, rhi;
+            window64<NX>(X, 8 * J, flo, fhi);
+            window64<NX>(Xr, 8 * (kKmersPerThread - 1 - J), rlo, rhi);
+            lt = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
+        } else {
+            lt = window<K, NX>(X, 8 * J) < window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - J));
+        }
+        // forward words at positions J + i, reverse words at 16 - J + i (same parity): the same pair rows
+        // of the forward block, or kBlkPairs + 8 - J rows further in the reverse block: one select, one add
+        const ScrBase b = scr_advance(fw, lt ? 0 : (kBlkPairs + 8 - J) * ROW);
+        uint32_t W[NWD + 1];
+        if constexpr ((J & 1) == 0) {
+            pairs_even<0>(b, W);
+        } else {  // one word, then pairs (the last pair may bring one word too many)
+            W[0] = scr_load1<(J >> 1) * ROW + 4>(b);
+            pairs_odd<0>(b, W);
+        }
+        return murmur_words<K>(W, hc);
+    }
+
+    // PANIB_K1_GROUP k-mers are hashed back to back before any of them is offered to the table: the survivor
+    // test ends a basic block, and inside one block ptxas interleaves the independent MurmurHash3 chains.
     static PANIB_HD void run(const uint32_t *X, const uint32_t *Xr, ScrBase fw, uint32_t vmask,
                              const HashConsts &hc, Emit &emit) {
         if constexpr (J < kKmersPerThread) {
-            bool lt;
-            if constexpr (WHOLE) {
-                uint32_t flo, fhi, rlo, rhi;
-                window64<NX>(X, 8 * J, flo, fhi);
-                window64<NX>(Xr, 8 * (kKmersPerThread - 1 - J), rlo, rhi);
-                lt = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);
-            } else {
-                lt = window<K, NX>(X, 8 * J) < window<K, NX>(Xr, 8 * (kKmersPerThread - 1 - J));
+            const Partial p0 = hash_one(X, Xr, fw, hc);
+#if PANIB_K1_GROUP == 2
+            const Partial p1 = KmerStep<K, J + 1, Emit>::hash_one(X, Xr, fw, hc);
+#endif
+            if (p0.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
+                if (vmask & (1u << J)) emit(p0);
             }
-            // forward words at positions J + i, reverse words at 16 - J + i (same parity): the same pair rows
-            // of the forward block, or kBlkPairs + 8 - J rows further in the reverse block: one select, one add
-            const ScrBase b = scr_advance(fw, lt ? 0 : (kBlkPairs + 8 - J) * ROW);
-            uint32_t W[NWD + 1];
-            if constexpr ((J & 1) == 0) {
-                pairs_even<0>(b, W);
-            } else {  // one word, then pairs (the last pair may bring one word too many)
-                W[0] = scr_load1<(J >> 1) * ROW + 4>(b);
-                pairs_odd<0>(b, W);
+#if PANIB_K1_GROUP == 2
+            if (p1.prefilter(hc)) {
+                if (vmask & (2u << J)) emit(p1);
             }
-            const Partial p = murmur_words<K>(W, hc);
-            if (p.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
-                if (vmask & (1u << J)) emit(p);
-            }
-            KmerStep<K, J + 1, Emit>::run(X, Xr, fw, vmask, hc, emit);
+#endif
+            KmerStep<K, J + PANIB_K1_GROUP, Emit>::run(X, Xr, fw, vmask, hc, emit);
         }
     }
 };

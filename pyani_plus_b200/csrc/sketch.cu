@@ -9,6 +9,9 @@
 // (kmer_hash.cuh), and the only global writes are the ~1/scaled surviving hashes, inserted into
 // value-range buckets of the genome's row so that a per-bucket sort yields the globally sorted,
 // duplicate-free sketch.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "kmer_hash.cuh"
 #include "pack.cuh"
@@ -68,16 +71,41 @@ struct GenomeSlot {
     uint64_t bmul;
     int32_t *flag;
     int nb;
+    int genome;
+};
+
+// Survivors of one K1 launch, parked instead of inserted: CTA b appends (hash, genome) to its own region
+// [b * cap, (b+1) * cap) of a caller-provided workspace (panib_set_workspace), the position coming from a
+// SHARED-memory counter, and sketch_scatter_kernel inserts them afterwards with every thread busy.  The hot
+// loop then never waits ~1 us for a global atomicCAS in a mostly idle warp (which is also what lets the
+// warps of a CTA drift apart between barriers).  A full region falls back to the direct insert.
+struct SurvivorBuf {
+    uint64_t *hash;     // [ctas * cap]
+    uint32_t *genome;   // [ctas * cap]
+    uint32_t *count;    // [ctas]
+    uint32_t cap;       // entries per CTA; 0 = no workspace: insert directly
 };
 
 struct EmitToTable {
     const GenomeSlot *slot;  // shared memory
     uint64_t max_hash;
     int32_t *status;
-    // survivor path of the fast kernel: finish the hash, exact test, insert
+    SurvivorBuf buf;
+    uint32_t *s_count;  // shared: survivors parked by this CTA
+    // survivor path of the fast kernel: finish the hash, exact test, park (or insert)
     __device__ __forceinline__ void operator()(const Partial &p) const {
         const uint64_t h = p.hash();
-        if (h <= max_hash) table_insert(slot->row, slot->nb, slot->bmul, h, slot->flag, status);
+        if (h > max_hash) return;
+        if (buf.cap) {
+            const uint32_t at = atomicAdd(s_count, 1u);
+            if (at < buf.cap) {
+                const size_t e = (size_t)blockIdx.x * buf.cap + at;
+                buf.hash[e] = h;
+                buf.genome[e] = (uint32_t)slot->genome;
+                return;
+            }
+        }
+        table_insert(slot->row, slot->nb, slot->bmul, h, slot->flag, status);
     }
 };
 
@@ -134,7 +162,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
                    const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
                    const HashConsts hc, const int32_t *__restrict__ nb,
                    const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
-                   int32_t *flags, int32_t *status, uint32_t *ticket) {
+                   int32_t *flags, int32_t *status, uint32_t *ticket, const SurvivorBuf surv) {
     // hc arrives as a kernel parameter (computed on the host): its 64-bit constants then sit in uniform
     // registers and feed the 3-input adds directly, instead of being folded into immediates one at a time
     using G_ = Geom<K>;
@@ -144,13 +172,18 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     __shared__ __align__(16) uint32_t rcp_[kSpStage];
     __shared__ GenomeSlot s_slot;
     __shared__ int64_t s_next;
+    __shared__ uint32_t s_nsurv;
     // per-thread ASCII scratch as pairs of words (kmer_hash.cuh: scr_index)
     extern __shared__ __align__(16) uint32_t scratch[];  // kK1DynSmem bytes
     constexpr int S = kTileBases / kCtaTile;
     n_tiles *= S;
     int64_t tile = tile_begin * S + blockIdx.x;
-    if (tile >= n_tiles) return;
+    if (tile >= n_tiles) {
+        if (surv.cap && threadIdx.x == 0) surv.count[blockIdx.x] = 0u;
+        return;
+    }
     const int tid = threadIdx.x;
+    if (tid == 0) s_nsurv = 0u;
     auto prefetch = [&](int64_t t, int b) {
         const uint32_t *gp = packed + t * (kCtaTile / 16);
         const uint32_t *gm = mask + t * (kCtaTile / 32);
@@ -172,7 +205,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     __syncthreads();
     int64_t next = ticket ? s_next : tile + gridDim.x;
     const int u = tid >> 2, a = tid & 3;
-    const EmitToTable emit{&s_slot, max_hash, status};
+    const EmitToTable emit{&s_slot, max_hash, status, surv, &s_nsurv};
     int g = 0;
     for (int it = 0; tile < n_tiles; ++it) {
         const int cur = it & 1;
@@ -187,7 +220,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
             s_next = ticket ? (next < n_tiles ? dyn_base + drawn : n_tiles) : next + gridDim.x;
         } else if (tid == 32) {
             g = find_genome(tile_off, n_genomes, tile / S, g);
-            s_slot = GenomeSlot{table + (size_t)g * row_stride, __ldg(bmul + g), flags + g, __ldg(nb + g)};
+            s_slot = GenomeSlot{table + (size_t)g * row_stride, __ldg(bmul + g), flags + g, __ldg(nb + g), g};
         }
         // phase A: items 0..255 one per thread, the halo by warp 2
         tile_expand_item<K>(sp, rcp, scratch, kThreadsK1, tid);
@@ -199,6 +232,22 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         hash_thread_kmers<K>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, emit);
         tile = next;
         next = s_next;  // written before the barrier above, overwritten after the next one
+    }
+    if (surv.cap) {
+        __syncthreads();
+        if (tid == 0) surv.count[blockIdx.x] = s_nsurv < surv.cap ? s_nsurv : surv.cap;
+    }
+}
+
+// the parked survivors of a K1 launch -> their genomes' bucketed rows.  grid = (chunks of a region, CTAs of K1)
+__global__ void __launch_bounds__(256)
+sketch_scatter_kernel(const SurvivorBuf surv, const int32_t *__restrict__ nb, const uint64_t *__restrict__ bmul,
+                      uint64_t *__restrict__ table, int64_t row_stride, int32_t *flags, int32_t *status) {
+    const uint32_t n = surv.count[blockIdx.y];
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const size_t e = (size_t)blockIdx.y * surv.cap + i;
+        const uint32_t g = surv.genome[e];
+        table_insert(table + (size_t)g * row_stride, __ldg(nb + g), __ldg(bmul + g), surv.hash[e], flags + g, status);
     }
 }
 
@@ -456,6 +505,53 @@ extern "C" int panib_pack_ascii(const uint8_t *d_ascii, int64_t n_bases, uint32_
     return check_launch("pack_ascii_kernel");
 }
 
+// ---- survivor workspace: registered per DEVICE by the caller (panib_set_workspace), owned by the caller.
+// Per device, not per stream: a CUDA graph capture runs on a stream of its own, and the captured kernels must
+// find the same scratch as the eager ones.  Sketch calls of one device are serialised by their callers.
+namespace {
+struct Workspace {
+    void *ptr;
+    int64_t bytes;
+};
+std::mutex g_ws_mutex;
+std::map<int, Workspace> g_ws;  // key: device ordinal
+}  // namespace
+
+extern "C" int panib_set_workspace(void *d_ptr, int64_t bytes) {
+    int dev = 0;
+    PANIB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    if (!d_ptr || bytes <= 0) g_ws.erase(dev);
+    else g_ws[dev] = Workspace{d_ptr, bytes};
+    return PANIB_OK;
+}
+
+// regions of `ctas` CTAs in the stream's workspace, sized for `bases` hashed at 1/scaled survival with 2x
+// head room; cap = 0 (direct inserts) when there is no workspace or it is too small to be worth it
+static SurvivorBuf survivor_regions(int ctas, int64_t bases, uint64_t max_hash) {
+    SurvivorBuf b{nullptr, nullptr, nullptr, 0u};
+    Workspace w{nullptr, 0};
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(g_ws_mutex);
+        auto it = g_ws.find(dev);
+        if (it != g_ws.end()) w = it->second;
+    }
+    if (!w.ptr || ctas <= 0) return b;
+    const double rate = ((double)max_hash + 1.0) / 18446744073709551616.0;  // survival probability of a k-mer
+    int64_t want = (int64_t)(2.0 * rate * (double)bases / ctas) + 1024;
+    const int64_t room = (w.bytes - 256 - (int64_t)ctas * 4) / ((int64_t)ctas * 12) / 2 * 2;  // even: 8-byte alignment
+    if (want > room) want = room;
+    if (want < 256 || want > 0x7FFFFFFF) return b;
+    char *base = static_cast<char *>(w.ptr);
+    b.hash = reinterpret_cast<uint64_t *>(base);
+    b.genome = reinterpret_cast<uint32_t *>(base + (size_t)ctas * want * 8);
+    b.count = reinterpret_cast<uint32_t *>(base + (size_t)ctas * want * 12);
+    b.cap = (uint32_t)want;
+    return b;
+}
+
 // launch K1 over tiles [tile_begin, tile_end) of the stream (table / flags already initialised)
 static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, const int64_t *d_tile_off,
                              int64_t n_genomes, int64_t tile_begin, int64_t tile_end, int k, uint32_t seed,
@@ -473,10 +569,14 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
     }
 #endif
     const HashConsts hc = make_hash_consts(seed, max_hash);
+    SurvivorBuf surv{nullptr, nullptr, nullptr, 0u};
+    int ctas = 0;
 #define PANIB_LAUNCH_K(KK)                                                                                   \
-    sketch_hash_kernel<KK><<<persistent_grid<KK>(n * (kTileBases / kCtaTile)), kThreadsK1, kK1DynSmem, st>>>( \
+    ctas = persistent_grid<KK>(n * (kTileBases / kCtaTile));                                                 \
+    surv = survivor_regions(ctas, n * (int64_t)kTileBases, max_hash);                                    \
+    sketch_hash_kernel<KK><<<ctas, kThreadsK1, kK1DynSmem, st>>>(                                            \
         d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, hc, d_nb, d_bmul,                \
-        d_table, row_stride, d_flags, d_status, ticket)
+        d_table, row_stride, d_flags, d_status, ticket, surv)
     switch (k) {
     case 21: PANIB_LAUNCH_K(21); break;
     case 31: PANIB_LAUNCH_K(31); break;
@@ -486,7 +586,12 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
                                                                   d_bmul, d_table, row_stride, d_flags, d_status);
     }
 #undef PANIB_LAUNCH_K
-    return check_launch("sketch_hash_kernel");
+    int rc = check_launch("sketch_hash_kernel");
+    if (rc || !surv.cap) return rc;
+    const unsigned gx = (unsigned)((surv.cap + 255) / 256 < 64 ? (surv.cap + 255) / 256 : 64);
+    sketch_scatter_kernel<<<dim3(gx, (unsigned)ctas), 256, 0, st>>>(surv, d_nb, d_bmul, d_table, row_stride, d_flags,
+                                                                    d_status);
+    return check_launch("sketch_scatter_kernel");
 }
 
 static int check_sketch_args(int k, int64_t row_stride) {

@@ -12,6 +12,7 @@ What the engine replaces in the reference: the two external commands of
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from pathlib import Path
 
@@ -40,6 +41,7 @@ class EngineError(RuntimeError):
 
 
 _lib: ctypes.CDLL | None = None
+_WORKSPACES: dict = {}  # device index -> (survivor scratch tensor registered with the library, frozen by a graph)
 
 
 def load_library() -> ctypes.CDLL:
@@ -80,6 +82,8 @@ def load_library() -> ctypes.CDLL:
     L.panib_sketch_ascii_host.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp, _vp]
     L.panib_sketch_ascii_host_hash_only.restype = _i32
     L.panib_sketch_ascii_host_hash_only.argtypes = [_vp, _vp, _i64, *sk_args, _vp, _vp, _vp]
+    L.panib_set_workspace.restype = _i32
+    L.panib_set_workspace.argtypes = [_vp, _i64]
     L.panib_host_threads.restype = _i32
     L.panib_pack_host.restype = _i32
     L.panib_pack_host.argtypes = [_vp, _i64, _vp, _vp, _i32]
@@ -328,8 +332,31 @@ class Engine:
             bufs["h_mask"] = torch.empty(plan.n_bases // 32, dtype=torch.int32, pin_memory=True)
         return bufs
 
+    def _ensure_workspace(self, plan: "StreamPlan") -> None:
+        """Survivor scratch of the sketch kernels on this device (``panib_set_workspace``): one per process
+        and device, shared by every ``Engine`` there, grown to what the largest stream planned so far needs
+        and never freed.  Once a CUDA graph has captured kernels that point at it, it is no longer replaced
+        (a too-small one only means K1 inserts directly, the results are the same)."""
+        if os.environ.get("PANIB_NO_WORKSPACE"):  # A/B knob: K1 then inserts survivors directly
+            return
+        need = int(2 * 12 * plan.n_bases / max(1, plan.scaled)) + (1 << 20)
+        key = self.device.index
+        have, frozen = _WORKSPACES.get(key, (None, False))
+        if (have is not None and have.numel() >= need) or frozen:
+            return
+        ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        _check(self.lib.panib_set_workspace(ws.data_ptr(), need))
+        _WORKSPACES[key] = (ws, False)
+
+    def freeze_workspace(self) -> None:
+        """Called before a CUDA graph captures sketch kernels: the scratch they point at must stay."""
+        key = self.device.index
+        if key in _WORKSPACES:
+            _WORKSPACES[key] = (_WORKSPACES[key][0], True)
+
     def alloc_table(self, plan: "StreamPlan") -> dict:
         torch = self.torch
+        self._ensure_workspace(plan)
         n = max(plan.n_genomes, 1)
         return {
             "table": torch.empty((n, plan.row_stride), dtype=torch.int64, device=self.device),

@@ -77,8 +77,13 @@ class SourmashStep:
                            method=self.k2_method)
         if marks is not None:
             marks[2].record()
+        # With several ranks ``ov`` is this rank's PARTIAL matrix (the pairs / hash range it owns; the ranks'
+        # matrices sum to the whole), so identity / cov_query are partial too: NaN -- which in a complete
+        # matrix means "no common hash" -- also marks every pair another rank computed.  Callers that want
+        # one complete result sum the integer matrices first (``multi_gpu.combine_partial``) and derive ANI
+        # from the sum (``run.intersect_sharded`` + ``engine.ani_host``); never sum the float matrices.
         ident, cov = eng.ani_device(ov, table)
-        self.out.update(table=table, ov=ov, identity=ident, cov_query=cov)
+        self.out.update(table=table, ov=ov, identity=ident, cov_query=cov, partial=self.world > 1)
         if to_host:
             torch = eng.torch
             for name, t in (("identity", ident), ("cov_query", cov), ("counts", table.counts)):
@@ -116,6 +121,7 @@ class SourmashStep:
         self.run(from_host=from_host, to_host=to_host)  # sets kernel attributes, allocates pinned buffers
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        self.eng.freeze_workspace()  # the captured kernels hold its address
         try:
             with torch.cuda.graph(graph):
                 self.enqueue(from_host=from_host, to_host=to_host)

@@ -457,3 +457,34 @@ def test_intersect_auto_picks_a_method_and_matches(eng) -> None:
     # rectangular calls cannot use the index
     with pytest.raises(ValueError, match="all-vs-all"):
         eng.intersect(table, table, method="index")
+
+
+def test_survivor_workspace_and_direct_insert_agree(eng, monkeypatch: pytest.MonkeyPatch) -> None:
+    """K1 parks survivors in the registered workspace and a second kernel inserts them; without a workspace
+    (or when a CTA's region overflows) it inserts directly from the hashing loop.  Same sketches either way,
+    also for dense sketches (scaled=20: every CTA region overflows into the direct path) and equal to the oracle."""
+    from pyani_plus_b200 import engine as _eng
+
+    n, length, k = 5, 600_000, 31
+    d_ascii, tile_off = eng.synth_ascii_stream(SEED, 7, n, length)
+    for scaled in (1000, 20):
+        with_ws = eng.sketch_ascii_stream(d_ascii, tile_off, k, scaled, from_host=False).to_host()
+        assert eng.device.index in _eng._WORKSPACES  # noqa: SLF001
+        _eng._check(eng.lib.panib_set_workspace(None, 0))  # noqa: SLF001
+        monkeypatch.setattr(eng, "_ensure_workspace", lambda plan: None)
+        direct = eng.sketch_ascii_stream(d_ascii, tile_off, k, scaled, from_host=False).to_host()
+        monkeypatch.undo()
+        _eng._WORKSPACES.pop(eng.device.index, None)  # noqa: SLF001  the next alloc_table registers a fresh one
+        # a workspace far too small for the survivors: regions overflow, the rest is inserted directly
+        import torch
+
+        tiny = torch.empty(1 << 16, dtype=torch.uint8, device=eng.device)
+        _eng._check(eng.lib.panib_set_workspace(tiny.data_ptr(), tiny.numel()))  # noqa: SLF001
+        monkeypatch.setattr(eng, "_ensure_workspace", lambda plan: None)
+        overflow = eng.sketch_ascii_stream(d_ascii, tile_off, k, scaled, from_host=False).to_host()
+        monkeypatch.undo()
+        _eng._check(eng.lib.panib_set_workspace(None, 0))  # noqa: SLF001
+        want_h, want_c = oracle.synth_sketch_batch(SEED, 7, n, length, k, scaled)
+        for g in range(n):
+            want = want_h[g, : want_c[g]].tolist()
+            assert with_ws[g].tolist() == want and direct[g].tolist() == want and overflow[g].tolist() == want, (scaled, g)
