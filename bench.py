@@ -346,7 +346,8 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     tab = eng.alloc_table(plan)
     # e2e needs the whole ASCII stream in pinned host memory; skipped (null) for streams > 12 GB
     do_e2e = plan.n_bases <= (12 << 30) and not args.no_e2e
-    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8) if do_e2e else None  # what a FASTA reader hands over
+    # what a FASTA reader hands over: the ASCII stream in page-locked host memory
+    h_ascii = torch.empty(plan.n_bases, dtype=torch.uint8, pin_memory=True) if do_e2e else None
     batch = 256  # genomes generated + packed per pass, so that the ASCII form is never fully resident
     for b0 in range(0, per_rank, batch):
         b1 = min(per_rank, b0 + batch)
@@ -367,6 +368,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     if do_e2e:  # pinned staging of the packed form: the host threads pack into it inside every e2e step
         bufs["h_packed"] = torch.empty(plan.n_bases // 16, dtype=torch.int32, pin_memory=True)
         bufs["h_mask"] = torch.empty(plan.n_bases // 32, dtype=torch.int32, pin_memory=True)
+        eng.add_ingest_scratch(plan, bufs)
 
     n_rows = per_rank * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -447,8 +449,10 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         wall = time.perf_counter() - wall0
         clocks = sampler.stop() if rank == 0 else None
         launches = eng.launch_count() - launches0 + (steps * per_step_launches[from_host] if graph else 0)
-        stats = torch.tensor([sum(tot), sum(t_k1), sum(t_gather), sum(t_k2), float(launches)],
-                             dtype=torch.float64, device=dev)
+        ing = eng.ingest_last() if from_host else {"h2d_bytes": 0, "chunks": 0, "chunks_as_ascii": 0, "dirty_tiles": 0}
+        stats = torch.tensor([sum(tot), sum(t_k1), sum(t_gather), sum(t_k2), float(launches),
+                              float(ing["h2d_bytes"]), float(ing["chunks"]), float(ing["chunks_as_ascii"]),
+                              float(ing["dirty_tiles"])], dtype=torch.float64, device=dev)
         if world > 1:
             mx = stats.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -457,7 +461,9 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
             stats = torch.cat([mx[:4], sm[4:]])
         s = stats.cpu().tolist()
         return {"ms": s[0] / steps, "k1_ms": s[1] / steps, "gather_ms": s[2] / steps, "k2_ms": s[3] / steps,
-                "launches": int(s[4]), "wall_s": wall, "clocks": clocks}
+                "launches": int(s[4]), "wall_s": wall, "clocks": clocks,
+                "ingest": {"h2d_bytes": int(s[5]), "chunks": int(s[6]), "chunks_as_ascii": int(s[7]),
+                           "dirty_tiles": int(s[8])}}
 
     eager_t = timed_loop(False, args.steps, args.warmup)  # stage breakdown (events between the stages)
     dev_t = timed_loop(False, args.steps, args.warmup, graph=True) if graphed.get(False) else eager_t
@@ -585,10 +591,14 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         "cpu_baseline_detail": ({"sketch_gbp_s": cpu["sketch_gbp_s"],
                                  "pairs_per_s_intersect": cpu["pairs_per_s_intersect"]} if cpu else None),
         "e2e": ({"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_t["ms"],
-                 "h2d_bytes_per_step": int(plan.n_bases // 16 * 4 + plan.n_bases // 32 * 4) * world,
+                 "h2d_bytes_per_step": e2e_t["ingest"]["h2d_bytes"],
                  "host_ascii_bytes_per_step": int(plan.n_bases) * world,
+                 "ingest": {**e2e_t["ingest"],
+                            "what": "counted by the library in the last timed step, summed over ranks: packed chunks "
+                                    "(0.25 B/base) + masks of the tiles holding invalid bases + chunks sent as ASCII "
+                                    "(1 B/base) from the tail of the stream while the link would otherwise idle"},
                  "host_pack": {"threads_per_rank": min(stepper.host_threads, int(eng.lib.panib_host_threads())),
-                               "what": "ASCII -> 2-bit + validity mask on the host threads (AVX-512/AVX2), "
+                               "what": "ASCII -> 2-bit + dirty-tile masks on the host threads (AVX-512/AVX2), "
                                        "inside the timed step, pipelined with the copies and K1"},
                  "d2h_bytes_per_step": int(2 * n_rows * n_rows * 8 + n_rows * 4) * world,
                  "stage_ms": {"h2d_pack_k1": e2e_t["k1_ms"], "allgather": e2e_t["gather_ms"],

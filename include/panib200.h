@@ -167,14 +167,33 @@ PANIB_API int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t 
 PANIB_API int panib_host_threads(void);
 PANIB_API int panib_pack_host(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
                     int threads);
+/* Sparse-mask form (what the ingest pipeline runs on its pool): n_bases a multiple of PANIB_TILE_BASES;
+ * h_tile_dirty[t] = 1 when tile t holds an invalid base, and only then are the tile's PANIB_TILE_BASES/32 mask
+ * words written to h_mask (a clean tile's mask is all zero and is never touched). */
+PANIB_API int panib_pack_host_tiles(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
+                          uint8_t *h_tile_dirty, int threads);
 
 /* Packed host-buffer form of panib_sketch_stream: the ingest pipeline.  h_packed / h_mask are (pinned) host
- * buffers of n_bases/16 and n_bases/32 words.  With h_ascii != NULL the ASCII stream is packed into them by
- * the host threads chunk by chunk, overlapped with the host->device copies of the packed chunks and with K1
- * on the chunks already copied; with h_ascii == NULL they already hold the packed stream.  d_counts == NULL
- * skips the finalize step (rows stay bucketed hash sets, as after panib_sketch_hash_only).  The call returns
- * when all host work is done and all device work is enqueued on `stream`. */
+ * buffers of n_bases/16 and n_bases/32 words.  With h_ascii == NULL they already hold the packed stream and are
+ * copied as they are.  With h_ascii != NULL the ASCII stream is packed into them by the host threads chunk by
+ * chunk, overlapped with the host->device copies of the packed chunks and with K1 on the chunks already on the
+ * device; h_packed / h_mask are then scratch (their content after the call is unspecified).
+ * d_scratch (device, scratch_bytes; may be NULL / 0) widens the pipeline, panib_ingest_scratch_bytes(n_bases)
+ * tells how much serves everything:
+ *   - with room for the mask staging ring the validity mask is sent sparsely: only the 512-byte masks of tiles
+ *     that hold an invalid base cross PCIe (0.25 instead of 0.375 byte per base), a kernel scatters them;
+ *   - with room for at least one more chunk of ASCII, and h_ascii page-locked, chunks are also taken from the
+ *     END of the stream as plain ASCII whenever the link would otherwise wait for the host threads, and packed
+ *     on the GPU: host cores and link both stay busy whatever their relative speeds.
+ * d_counts == NULL skips the finalize step (rows stay bucketed hash sets, as after panib_sketch_hash_only).
+ * The call returns when all host work is done and all device work is enqueued on `stream`.  The sketches do
+ * not depend on which way a chunk travelled. */
+PANIB_API int64_t panib_ingest_scratch_bytes(int64_t n_bases);
+/* What the calling thread's last panib_sketch_packed_host moved: out4 = {bytes copied host->device, chunks,
+ * chunks that travelled as ASCII, tiles whose mask was sent}. */
+PANIB_API int panib_ingest_last(int64_t *out4);
 PANIB_API int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_packed, uint32_t *h_mask, int64_t n_bases,
+                             uint8_t *d_scratch, int64_t scratch_bytes,
                              uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,
                              int64_t n_genomes, int64_t n_tiles, int k, uint32_t seed, uint64_t max_hash,
                              const int32_t *d_nb, const uint64_t *d_bmul, uint64_t *d_table,

@@ -11,6 +11,8 @@
 // duplicate-free sketch.
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 #include "kmer_hash.cuh"
@@ -768,21 +770,71 @@ extern "C" int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t
 // ------------------------------------------------------------------------------------------------
 // Packed host-buffer form: the ingest pipeline of the drop-in path.  The genomes arrive as an ASCII base
 // stream in host memory (h_ascii) or already packed (h_ascii == NULL).  The stream is cut into chunks of
-// whole tiles; the pool of host threads (hostpack.cpp) packs chunk c+1 into the pinned h_packed / h_mask
-// while chunk c crosses PCIe (0.375 byte per base instead of 1) on the copy stream and chunk c-1 is hashed
-// by K1 on the caller's stream.  d_counts == NULL leaves the rows as bucketed hash sets (the caller
-// finalizes: panib_sketch_finalize or, on several GPUs, panib_sketch_finalize_gather).
+// whole tiles and worked on from BOTH ends:
+//   * the pool of host threads (hostpack.cpp) packs chunks from the front into the pinned h_packed; a packed
+//     chunk crosses PCIe as 0.25 byte per base.  The validity mask is not sent densely: the pool flags the
+//     tiles that hold an invalid base ("dirty": genome ends, record separators, N runs), only their 512-byte
+//     masks are copied (compacted in place in h_mask, ids behind them) and a small kernel scatters them over
+//     the zeroed mask of the chunk;
+//   * whenever the link would otherwise idle (the next packed chunk is not ready and at most one copy is in
+//     flight) and h_ascii is page-locked, the submitting thread takes the LAST chunk no pool thread has touched
+//     and sends it as ASCII (1 byte per base) into a slot of d_scratch, where the GPU packs it (K0).
+// So the host cores and the link are both kept busy whatever their relative speeds (1 or 8 GPUs per host, 4 or
+// 32 cores per GPU), and K1 runs on every chunk as soon as it is on the device, in arrival order: the tile at
+// a chunk boundary (its k-1 halo lives in the next chunk) is hashed with whichever neighbour arrives second.
+// d_counts == NULL leaves the rows as bucketed hash sets (the caller finalizes: panib_sketch_finalize or, on
+// several GPUs, panib_sketch_finalize_gather).
 // ------------------------------------------------------------------------------------------------
 namespace panib {
 struct HostPackJob;
 HostPackJob *host_pack_start(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
-                             int64_t bases_per_block, int threads);
-void host_pack_wait_prefix(HostPackJob *hp, int64_t blocks);
+                             int64_t bases_per_block, int threads, uint8_t *tile_dirty, int64_t blocks_per_chunk);
+bool host_pack_chunk_ready(HostPackJob *hp, int64_t c);
+bool host_pack_claim_raw(HostPackJob *hp, int64_t c);
+bool host_pack_help(HostPackJob *hp);
 void host_pack_finish(HostPackJob *hp);
 }  // namespace panib
 
+constexpr int kIngestMaxChunks = 64;
+constexpr int64_t kIngestBlockTiles = 64;  // packing block: 64 tiles = 256 Ki bases
+constexpr int kIngestMaskSlots = 3, kIngestRawSlots = 3;
+constexpr int kMaskWords = kTileBases / 32;  // mask words per tile
+
+static int64_t ingest_chunk_tiles(int64_t total_tiles) {
+    // chunks of whole packing blocks, >= 512 tiles (2 Mi bases) each, at most kIngestMaxChunks
+    int64_t per = (total_tiles + kIngestMaxChunks - 1) / kIngestMaxChunks;
+    if (per < 512) per = 512;
+    return (per + kIngestBlockTiles - 1) / kIngestBlockTiles * kIngestBlockTiles;
+}
+
+extern "C" int64_t panib_ingest_scratch_bytes(int64_t n_bases) {
+    if (n_bases <= 0) return 0;
+    const int64_t per = ingest_chunk_tiles(n_bases / kTileBases);
+    return per * ((int64_t)kIngestMaskSlots * kMaskWords * 4 + (int64_t)kIngestRawSlots * kTileBases);
+}
+
+// what the last panib_sketch_packed_host call of this thread moved: {bytes host->device, chunks, chunks sent as
+// ASCII, dirty tiles}
+static thread_local int64_t g_ingest_last[4] = {0, 0, 0, 0};
+extern "C" int panib_ingest_last(int64_t *out4) {
+    if (!out4) return PANIB_E_ARG;
+    for (int i = 0; i < 4; i++) out4[i] = g_ingest_last[i];
+    return PANIB_OK;
+}
+
+// staging = [nd x 128 mask words][nd tile ids]: one warp moves one dirty tile's mask to its place
+__global__ void __launch_bounds__(256)
+mask_scatter_kernel(const uint32_t *__restrict__ staging, int nd, uint32_t *__restrict__ mask) {
+    const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= nd) return;
+    const uint32_t tile = staging[(size_t)nd * kMaskWords + w];
+    const uint4 v = reinterpret_cast<const uint4 *>(staging + (size_t)w * kMaskWords)[lane];
+    reinterpret_cast<uint4 *>(mask + (size_t)tile * kMaskWords)[lane] = v;
+}
+
 extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_packed, uint32_t *h_mask,
-                                        int64_t n_bases, uint32_t *d_packed, uint32_t *d_mask,
+                                        int64_t n_bases, uint8_t *d_scratch, int64_t scratch_bytes,
+                                        uint32_t *d_packed, uint32_t *d_mask,
                                         const int64_t *d_tile_off, int64_t n_genomes, int64_t n_tiles, int k,
                                         uint32_t seed, uint64_t max_hash, const int32_t *d_nb,
                                         const uint64_t *d_bmul, uint64_t *d_table, int64_t row_stride,
@@ -801,29 +853,56 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     if (n_genomes <= 0 || n_tiles <= 0) return PANIB_OK;
     cudaStream_t st = (cudaStream_t)stream;
 
-    constexpr int kMaxChunks = 64;
-    constexpr int64_t kBlockTiles = 64;  // packing block: 64 tiles = 256 Ki bases
-    static thread_local cudaStream_t copy_stream = nullptr;
-    static thread_local cudaEvent_t ev_copied[kMaxChunks], ev_ready = nullptr;
-    static thread_local int ev_device = -1;
+    struct Res {
+        cudaStream_t copy_stream = nullptr;
+        cudaEvent_t copied[kIngestMaxChunks], ready = nullptr, mask_free[kIngestMaskSlots], raw_free[kIngestRawSlots];
+        int device = -1;
+        std::vector<uint8_t> dirty;
+        std::vector<uint32_t> ids;
+    };
+    static thread_local Res R;
     int dev = 0;
     PANIB_CUDA(cudaGetDevice(&dev));
-    if (!copy_stream || ev_device != dev) {
-        PANIB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < kMaxChunks; i++)
-            PANIB_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
-        PANIB_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
-        ev_device = dev;
+    if (!R.copy_stream || R.device != dev) {
+        PANIB_CUDA(cudaStreamCreateWithFlags(&R.copy_stream, cudaStreamNonBlocking));
+        for (auto &e : R.copied) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : R.mask_free) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : R.raw_free) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        PANIB_CUDA(cudaEventCreateWithFlags(&R.ready, cudaEventDisableTiming));
+        R.device = dev;
     }
-    // chunks of whole packing blocks, >= 512 tiles (2 Mi bases) each, at most kMaxChunks
-    const int64_t total_tiles = n_tiles + 1;
-    int64_t per = (total_tiles + kMaxChunks - 1) / kMaxChunks;
-    if (per < 512) per = 512;
-    per = (per + kBlockTiles - 1) / kBlockTiles * kBlockTiles;
+    cudaStream_t cs = R.copy_stream;
+    const int64_t total_tiles = n_tiles + 1;  // the trailing pad tile rides with the last chunk
+    const int64_t per = ingest_chunk_tiles(total_tiles);
     const int n_chunks = (int)((total_tiles + per - 1) / per);
 
+    // ---- what the caller's scratch allows
+    const int64_t mask_slot = per * kMaskWords * 4, raw_slot = per * (int64_t)kTileBases;
+    auto env_off = [](const char *name) {
+        const char *e = getenv(name);
+        return e && e[0] == '0';
+    };
+    bool sparse = h_ascii && d_scratch && scratch_bytes >= kIngestMaskSlots * mask_slot && !env_off("PANIB_INGEST_SPARSE");
+    int raw_slots = 0;
+    const char *raw_env = getenv("PANIB_INGEST_RAW");  // 0 = never, 2 = whenever a chunk is free (tests); default: idle link
+    const bool raw_eager = raw_env && raw_env[0] == '2';
+    if (sparse && !env_off("PANIB_INGEST_RAW")) {
+        const int64_t room = (scratch_bytes - kIngestMaskSlots * mask_slot) / raw_slot;
+        raw_slots = (int)(room < kIngestRawSlots ? room : kIngestRawSlots);
+        if (raw_slots > 0) {  // an asynchronous copy needs page-locked memory: pageable ASCII stays with the pool
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, h_ascii) != cudaSuccess || attr.type != cudaMemoryTypeHost) raw_slots = 0;
+            cudaGetLastError();
+        }
+    }
+    uint8_t *d_mask_stage = d_scratch, *d_raw = d_scratch ? d_scratch + kIngestMaskSlots * mask_slot : nullptr;
+
     HostPackJob *job = nullptr;
-    if (h_ascii) job = host_pack_start(h_ascii, n_bases, h_packed, h_mask, kBlockTiles * kTileBases, host_threads);
+    if (h_ascii) {
+        if (sparse) R.dirty.assign((size_t)total_tiles, 0);
+        job = host_pack_start(h_ascii, n_bases, h_packed, h_mask, kIngestBlockTiles * kTileBases, host_threads,
+                              sparse ? R.dirty.data() : nullptr, per / kIngestBlockTiles);
+    }
     auto fail = [&](int code) {
         if (job) host_pack_finish(job);
         return code;
@@ -839,26 +918,124 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     PANIB_CUDA_JOB(cudaMemsetAsync(d_table, 0xFF, (size_t)n_genomes * row_stride * sizeof(uint64_t), st));
     PANIB_CUDA_JOB(cudaMemsetAsync(d_flags, 0, (size_t)n_genomes * sizeof(int32_t), st));
     // the copy stream must not overwrite d_packed / d_mask while earlier work on `st` may still read them
-    PANIB_CUDA_JOB(cudaEventRecord(ev_ready, st));
-    PANIB_CUDA_JOB(cudaStreamWaitEvent(copy_stream, ev_ready, 0));
-    int64_t hashed = 0;  // tiles [0, hashed) are done
-    for (int c = 0; c < n_chunks; c++) {
+    PANIB_CUDA_JOB(cudaEventRecord(R.ready, st));
+    PANIB_CUDA_JOB(cudaStreamWaitEvent(cs, R.ready, 0));
+
+    int64_t moved[4] = {0, n_chunks, 0, 0};
+    uint8_t arrived[kIngestMaxChunks] = {0};
+    int inflight[kIngestMaxChunks], n_inflight = 0;  // chunks whose copies are enqueued and not yet seen complete
+    int mask_used = 0, raw_used = 0;                 // slots handed out so far (ring position = count % slots)
+    // K1 over the tiles of chunk c that have everything they need on the device (stream order on `st`)
+    auto hash_chunk = [&](int c) -> int {
         const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles;
-        if (job) host_pack_wait_prefix(job, (t1 + kBlockTiles - 1) / kBlockTiles);
+        arrived[c] = 1;
+        const int64_t from = t0 - ((c > 0 && arrived[c - 1]) ? 1 : 0);
+        int64_t upto = (c == n_chunks - 1 || arrived[c + 1]) ? t1 : t1 - 1;  // halo of tile t1-1 is in the next chunk
+        if (upto > n_tiles) upto = n_tiles;
+        if (upto <= from) return PANIB_OK;
+        return launch_hash_range(d_packed, d_mask, d_tile_off, n_genomes, from, upto, k, seed, max_hash, d_nb, d_bmul,
+                                 d_table, row_stride, d_flags, d_status, st);
+    };
+    auto send_packed = [&](int c) -> int {
+        const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles, n = t1 - t0;
         PANIB_CUDA_JOB(cudaMemcpyAsync(d_packed + t0 * (kTileBases / 16), h_packed + t0 * (kTileBases / 16),
-                                       (size_t)(t1 - t0) * (kTileBases / 4), cudaMemcpyHostToDevice, copy_stream));
-        PANIB_CUDA_JOB(cudaMemcpyAsync(d_mask + t0 * (kTileBases / 32), h_mask + t0 * (kTileBases / 32),
-                                       (size_t)(t1 - t0) * (kTileBases / 8), cudaMemcpyHostToDevice, copy_stream));
-        PANIB_CUDA_JOB(cudaEventRecord(ev_copied[c], copy_stream));
-        PANIB_CUDA_JOB(cudaStreamWaitEvent(st, ev_copied[c], 0));
-        const int64_t upto = c == n_chunks - 1 ? n_tiles : t1 - 1;  // halo of tile t1-1 is in the next chunk
-        rc = launch_hash_range(d_packed, d_mask, d_tile_off, n_genomes, hashed, upto, k, seed, max_hash, d_nb,
-                               d_bmul, d_table, row_stride, d_flags, d_status, st);
-        if (rc) return fail(rc);
-        if (upto > hashed) hashed = upto;
+                                       (size_t)n * (kTileBases / 4), cudaMemcpyHostToDevice, cs));
+        moved[0] += n * (kTileBases / 4);
+        uint32_t *hm = h_mask + t0 * kMaskWords, *dm = d_mask + t0 * kMaskWords;
+        int nd = 0, slot = -1;
+        bool scatter = false;
+        if (!job || !sparse) {  // dense mask (already packed input, or no scratch for the sparse form)
+            PANIB_CUDA_JOB(cudaMemcpyAsync(dm, hm, (size_t)n * kMaskWords * 4, cudaMemcpyHostToDevice, cs));
+            moved[0] += n * kMaskWords * 4;
+        } else {
+            const uint8_t *dirty = R.dirty.data() + t0;
+            for (int64_t t = 0; t < n; t++) nd += dirty[t];
+            if ((int64_t)nd * (kMaskWords + 1) > n * kMaskWords) {  // (nearly) every tile: the region IS the dense mask
+                for (int64_t t = 0; t < n; t++)
+                    if (!dirty[t]) memset(hm + t * kMaskWords, 0, kMaskWords * 4);
+                PANIB_CUDA_JOB(cudaMemcpyAsync(dm, hm, (size_t)n * kMaskWords * 4, cudaMemcpyHostToDevice, cs));
+            } else {
+                PANIB_CUDA_JOB(cudaMemsetAsync(dm, 0, (size_t)n * kMaskWords * 4, cs));
+                if (nd) {  // compact the dirty tiles' masks to the front of the region, their ids behind them
+                    R.ids.clear();
+                    int64_t at = 0;
+                    for (int64_t t = 0; t < n; t++) {
+                        if (!dirty[t]) continue;
+                        if (t != at) memmove(hm + at * kMaskWords, hm + t * kMaskWords, kMaskWords * 4);
+                        R.ids.push_back((uint32_t)(t0 + t));
+                        at++;
+                    }
+                    memcpy(hm + (int64_t)nd * kMaskWords, R.ids.data(), (size_t)nd * 4);
+                    slot = mask_used % kIngestMaskSlots;
+                    if (mask_used >= kIngestMaskSlots) PANIB_CUDA_JOB(cudaStreamWaitEvent(cs, R.mask_free[slot], 0));
+                    mask_used++;
+                    PANIB_CUDA_JOB(cudaMemcpyAsync(d_mask_stage + slot * mask_slot, hm, (size_t)nd * (kMaskWords + 1) * 4,
+                                                   cudaMemcpyHostToDevice, cs));
+                    moved[0] += (int64_t)nd * (kMaskWords + 1) * 4;
+                    moved[3] += nd;
+                    scatter = true;
+                }
+            }
+        }
+        PANIB_CUDA_JOB(cudaEventRecord(R.copied[c], cs));
+        PANIB_CUDA_JOB(cudaStreamWaitEvent(st, R.copied[c], 0));
+        if (scatter) {
+            mask_scatter_kernel<<<(unsigned)((nd + 7) / 8), 256, 0, st>>>(
+                reinterpret_cast<const uint32_t *>(d_mask_stage + slot * mask_slot), nd, d_mask);
+            const int rc2 = check_launch("mask_scatter_kernel");
+            if (rc2) return fail(rc2);
+            PANIB_CUDA_JOB(cudaEventRecord(R.mask_free[slot], st));
+        }
+        inflight[n_inflight++] = c;
+        const int rc2 = hash_chunk(c);
+        return rc2 ? fail(rc2) : PANIB_OK;
+    };
+    auto send_raw = [&](int c) -> int {
+        const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles, n = t1 - t0;
+        const int slot = raw_used % raw_slots;
+        if (raw_used >= raw_slots) PANIB_CUDA_JOB(cudaStreamWaitEvent(cs, R.raw_free[slot], 0));
+        raw_used++;
+        uint8_t *dst = d_raw + slot * raw_slot;
+        PANIB_CUDA_JOB(cudaMemcpyAsync(dst, h_ascii + t0 * kTileBases, (size_t)n * kTileBases, cudaMemcpyHostToDevice, cs));
+        moved[0] += n * kTileBases;
+        moved[2] += 1;
+        PANIB_CUDA_JOB(cudaEventRecord(R.copied[c], cs));
+        PANIB_CUDA_JOB(cudaStreamWaitEvent(st, R.copied[c], 0));
+        int rc2 = panib_pack_ascii(dst, n * kTileBases, d_packed + t0 * (kTileBases / 16), d_mask + t0 * kMaskWords, stream);
+        if (rc2) return fail(rc2);
+        PANIB_CUDA_JOB(cudaEventRecord(R.raw_free[slot], st));
+        inflight[n_inflight++] = c;
+        rc2 = hash_chunk(c);
+        return rc2 ? fail(rc2) : PANIB_OK;
+    };
+
+    int head = 0, tail = n_chunks;  // chunks [head, tail) have not been sent yet
+    while (head < tail) {
+        if (!job || host_pack_chunk_ready(job, head)) {
+            rc = send_packed(head++);
+            if (rc) return rc;
+            continue;
+        }
+        if (raw_slots > 0) {  // the next packed chunk is not ready: is the link about to idle?
+            while (n_inflight > 0 && cudaEventQuery(R.copied[inflight[0]]) == cudaSuccess) {
+                for (int i = 1; i < n_inflight; i++) inflight[i - 1] = inflight[i];
+                n_inflight--;
+            }
+            cudaGetLastError();  // cudaErrorNotReady is not an error
+            if (n_inflight <= 1 || raw_eager) {
+                if (tail - 1 > head && host_pack_claim_raw(job, tail - 1)) {
+                    rc = send_raw(--tail);
+                    if (rc) return rc;
+                    continue;
+                }
+                raw_slots = 0;  // the pool has reached the tail: everything left is being packed
+            }
+        }
+        if (!host_pack_help(job)) std::this_thread::yield();
     }
 #undef PANIB_CUDA_JOB
     if (job) host_pack_finish(job);
+    for (int i = 0; i < 4; i++) g_ingest_last[i] = moved[i];
     if (!d_counts) return PANIB_OK;
     return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, d_status, stream);
 }

@@ -87,9 +87,15 @@ def load_library() -> ctypes.CDLL:
     L.panib_host_threads.restype = _i32
     L.panib_pack_host.restype = _i32
     L.panib_pack_host.argtypes = [_vp, _i64, _vp, _vp, _i32]
+    L.panib_pack_host_tiles.restype = _i32
+    L.panib_pack_host_tiles.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32]
     L.panib_sketch_packed_host.restype = _i32
-    L.panib_sketch_packed_host.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _u32, _u64, _vp, _vp,
-                                           _vp, _i64, _vp, _vp, _vp, _i32, _vp]
+    L.panib_sketch_packed_host.argtypes = [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _u32, _u64,
+                                           _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]
+    L.panib_ingest_scratch_bytes.restype = _i64
+    L.panib_ingest_scratch_bytes.argtypes = [_i64]
+    L.panib_ingest_last.restype = _i32
+    L.panib_ingest_last.argtypes = [_vp]
     L.panib_sketch_finalize_gather.restype = _i32
     L.panib_sketch_finalize_gather.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i32, _i32,
                                                _i64, _vp]
@@ -330,7 +336,14 @@ class Engine:
         if host_packed:
             bufs["h_packed"] = torch.empty(plan.n_bases // 16, dtype=torch.int32, pin_memory=True)
             bufs["h_mask"] = torch.empty(plan.n_bases // 32, dtype=torch.int32, pin_memory=True)
+            self.add_ingest_scratch(plan, bufs)
         return bufs
+
+    def add_ingest_scratch(self, plan: "StreamPlan", bufs: dict) -> None:
+        """Device scratch of the ingest pipeline (``panib_ingest_scratch_bytes``): staging of the sparse
+        validity mask and of the chunks that cross PCIe as plain ASCII."""
+        need = int(self.lib.panib_ingest_scratch_bytes(plan.n_bases))
+        bufs["ingest_scratch"] = self.torch.empty(max(need, 1), dtype=self.torch.uint8, device=self.device)
 
     def _ensure_workspace(self, plan: "StreamPlan") -> None:
         """Survivor scratch of the sketch kernels on this device (``panib_set_workspace``): one per process
@@ -389,14 +402,24 @@ class Engine:
                     finalize: bool = True, threads: int = 0) -> None:
         """The ingest pipeline in one C-ABI call (``panib_sketch_packed_host``): the host threads pack the
         ASCII stream (a host tensor; ``None`` = ``bufs["h_packed"]`` / ``["h_mask"]`` are already filled)
-        chunk by chunk into the pinned buffers while earlier chunks are copied (0.375 byte per base) and
-        hashed.  Returns when the host work is done and the device work is enqueued; ``finalize=False``
+        chunk by chunk into the pinned buffers while earlier chunks are copied (0.25 byte per base plus the
+        masks of the tiles that hold invalid bases) and hashed; with ``bufs["ingest_scratch"]`` and a pinned
+        ``h_ascii`` chunks also travel as ASCII from the tail of the stream whenever the link would idle.  Returns when the host work is done and the device work is enqueued; ``finalize=False``
         leaves the rows bucketed (multi-GPU: ``finalize_gather`` follows)."""
         a = self._sketch_args(plan, bufs, tab, k, seed)
+        scratch = bufs.get("ingest_scratch")
         _check(self.lib.panib_sketch_packed_host(
             h_ascii.data_ptr() if h_ascii is not None else None, bufs["h_packed"].data_ptr(),
-            bufs["h_mask"].data_ptr(), plan.n_bases, *a[:12], a[12] if finalize else None, a[13], a[14], threads,
-            a[15]))
+            bufs["h_mask"].data_ptr(), plan.n_bases, scratch.data_ptr() if scratch is not None else None,
+            scratch.numel() if scratch is not None else 0, *a[:12], a[12] if finalize else None, a[13], a[14],
+            threads, a[15]))
+
+    def ingest_last(self) -> dict:
+        """What the last ``sketch_host`` call of this thread moved over PCIe (``panib_ingest_last``)."""
+        out = (ctypes.c_int64 * 4)()
+        _check(self.lib.panib_ingest_last(out))
+        return {"h2d_bytes": int(out[0]), "chunks": int(out[1]), "chunks_as_ascii": int(out[2]),
+                "dirty_tiles": int(out[3])}
 
     def hash_packed(self, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42) -> None:
         """K1 hashing only: rows are left as bucketed hash sets (finalize separately)."""

@@ -169,3 +169,40 @@ def test_pack_host_code_paths_agree(lib: ctypes.CDLL) -> None:
     assert lib.panib_host_threads() >= 1
     with pytest.raises(ValueError, match="multiple of 32"):
         engine.pack_host(a[:33])
+
+
+def test_pack_host_tiles_sparse_mask(lib: ctypes.CDLL) -> None:
+    """panib_pack_host_tiles (the form the ingest pipeline runs): the packed words of panib_pack_host, a dirty
+    flag for exactly the tiles that hold an invalid base, their 128 mask words written and a clean tile's
+    mask words left untouched -- unaligned buffers (no non-temporal stores) included."""
+    from pyani_plus_b200 import engine
+
+    engine.load_library()
+    tile = 4096
+    n_tiles = 64 * 3 + 17  # several pool blocks plus a ragged one
+    rng = np.random.default_rng(11)
+    a = rng.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), size=n_tiles * tile)
+    dirty_tiles = sorted({0, 5, 63, 64, 100, n_tiles - 1})
+    for t in dirty_tiles:
+        at = t * tile + int(rng.integers(0, tile - 40))
+        a[at: at + int(rng.integers(1, 40))] = ord("N")
+    a[5 * tile: 6 * tile] = ord("n")  # a whole tile of invalid bases
+    want_p, want_m = engine.pack_host(a, 0)
+    for threads, shift in ((0, 0), (1, 0), (3, 1)):
+        pbuf = np.zeros(a.size // 16 + 4, np.uint32)
+        mbuf = np.full(a.size // 32 + 4, 0xABABABAB, np.uint32)
+        got_p, got_m = pbuf[shift: shift + a.size // 16], mbuf[shift: shift + a.size // 32]
+        dirty = np.full(n_tiles, 7, np.uint8)
+        rc = lib.panib_pack_host_tiles(a.ctypes.data, a.size, got_p.ctypes.data, got_m.ctypes.data, dirty.ctypes.data,
+                                       threads)
+        assert rc == 0
+        assert (got_p == want_p).all()
+        assert np.flatnonzero(dirty).tolist() == dirty_tiles and set(dirty.tolist()) <= {0, 1}
+        gm, wm = got_m.reshape(n_tiles, tile // 32), want_m.reshape(n_tiles, tile // 32)
+        for t in range(n_tiles):
+            if dirty[t]:
+                assert (gm[t] == wm[t]).all(), t
+            else:
+                assert (gm[t] == 0xABABABAB).all() and not wm[t].any(), t
+    assert lib.panib_pack_host_tiles(a.ctypes.data, tile + 32, None, None, None, 0) != 0
+    assert lib.panib_ingest_scratch_bytes(0) == 0 and lib.panib_ingest_scratch_bytes(64 * tile * 1000) > 0

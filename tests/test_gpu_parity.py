@@ -348,9 +348,6 @@ def test_step_pipeline_eager_and_graph(eng) -> None:
     out = stepper.run(from_host=True, to_host=True)
     check(out)
     ident_eager = out["identity_host"].clone()
-    # the host pack inside the step wrote what the device pack kernel writes
-    assert torch.equal(bufs["h_packed"].to(eng.device), bufs["packed"])
-    assert torch.equal(bufs["h_mask"].to(eng.device), bufs["mask"])
     assert not stepper.capture(from_host=True, to_host=True)  # host work inside: not a graph
     assert stepper.capture(to_host=True)
     tab["table"].fill_(7)  # stale rows must be overwritten by the replay
@@ -366,7 +363,11 @@ def test_step_pipeline_eager_and_graph(eng) -> None:
     got = _eng.SketchTable(tab["table"], tab["counts"], k, scaled).to_host()
     for g in range(n):
         assert got[g].tolist() == want_h[g, : want_c[g]].tolist(), g
-    # already-packed host buffers (h_ascii = None): copy + K1 only
+    # already-packed host buffers (h_ascii = None): copy + K1 only (after a host-input step h_packed / h_mask
+    # are scratch, so fill them with the dense packed form first)
+    hp, hm = _eng.pack_host(h_ascii.numpy())
+    bufs["h_packed"].copy_(torch.from_numpy(hp.view(np.int32)))
+    bufs["h_mask"].copy_(torch.from_numpy(hm.view(np.int32)))
     tab["table"].fill_(7)
     eng.sketch_host(None, plan, bufs, tab, k)
     assert eng.check_status() == 0
@@ -488,3 +489,69 @@ def test_survivor_workspace_and_direct_insert_agree(eng, monkeypatch: pytest.Mon
         for g in range(n):
             want = want_h[g, : want_c[g]].tolist()
             assert with_ws[g].tolist() == want and direct[g].tolist() == want and overflow[g].tolist() == want, (scaled, g)
+
+
+def test_ingest_pipeline_paths_agree(eng, monkeypatch: pytest.MonkeyPatch) -> None:
+    """``panib_sketch_packed_host``: whichever way a chunk travels -- packed by the host threads with a sparse
+    or a dense validity mask, or as plain ASCII from the tail of the stream and packed by the GPU -- the device
+    ends up with the words and mask bits of the device pack kernel and with the oracle's sketches.  Genomes
+    with N runs, lower case and several records make many tiles dirty; one genome of only N makes a chunk
+    (nearly) all dirty, which takes the dense route inside the sparse form."""
+    import torch
+
+    from pyani_plus_b200 import engine as _eng
+
+    rng = np.random.default_rng(5)
+    k, scaled = 31, 100
+    genomes = []
+    for g in range(9):
+        recs = []
+        for _ in range(1 + g % 3):
+            seq = bytearray(oracle.synth_genome(SEED, 300 + g, 700_000 + 4096 * g))
+            for _ in range(g * 40):  # scattered N runs and lower-case stretches
+                at = int(rng.integers(0, len(seq) - 200))
+                n_run = int(rng.integers(1, 90))
+                seq[at: at + n_run] = b"N" * n_run
+                lo = int(rng.integers(0, len(seq) - 200))
+                seq[lo: lo + 50] = bytes(seq[lo: lo + 50]).lower()
+            recs.append(bytes(seq))
+        genomes.append(recs)
+    genomes.insert(4, [b"N" * 5_000_000])  # covers a whole chunk with nothing but invalid bases
+    from pyani_plus_b200 import stream as pstream
+
+    tile_off = pstream.plan_tiles([pstream.genome_stream_length(recs) for recs in genomes])
+    plan = eng.plan_stream(tile_off, scaled)
+    h_pageable = torch.empty(plan.n_bases, dtype=torch.uint8)
+    pstream.fill_ascii_stream(h_pageable.numpy(), tile_off, genomes)
+    h_pinned = h_pageable.pin_memory()
+    bufs = eng.alloc_stream_buffers(plan, ascii_too=True, host_packed=True)
+    tab = eng.alloc_table(plan)
+    eng.pack(h_pinned.to(eng.device), plan, bufs)
+    want_packed, want_mask = bufs["packed"].clone(), bufs["mask"].clone()
+    want = [oracle.sketch_records(recs, k, scaled) for recs in genomes]
+
+    def run(h_ascii, **env: str) -> None:
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        bufs["packed"].fill_(-1)
+        bufs["mask"].fill_(0x55555555)
+        tab["table"].fill_(7)
+        eng.sketch_host(h_ascii, plan, bufs, tab, k)
+        assert eng.check_status() == 0
+        for key in env:
+            monkeypatch.delenv(key)
+        assert torch.equal(bufs["packed"], want_packed), env
+        assert torch.equal(bufs["mask"], want_mask), env
+        got = _eng.SketchTable(tab["table"], tab["counts"], k, scaled).to_host()
+        for g, w in enumerate(want):
+            assert got[g].tolist() == w.tolist(), (env, g)
+
+    run(h_pageable)                                  # sparse mask, host threads only (pageable ASCII)
+    run(h_pinned)                                    # + raw chunks whenever the link would idle
+    run(h_pinned, PANIB_INGEST_RAW="2")              # raw chunks from the tail as long as any is free
+    run(h_pinned, PANIB_INGEST_RAW="0")              # sparse mask only
+    run(h_pinned, PANIB_INGEST_SPARSE="0")           # dense mask, in order
+    scratch = bufs.pop("ingest_scratch")             # no device scratch at all: dense mask, in order
+    run(h_pinned)
+    bufs["ingest_scratch"] = scratch[: scratch.numel() // 8]  # room for the mask ring only
+    run(h_pinned, PANIB_INGEST_RAW="2")
