@@ -158,6 +158,119 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #endif
 constexpr int kSpStage = kSpLead + kTileWords;  // lead-in + tile + halo words of one staging buffer
 
+#ifndef PANIB_K1_WARP
+#define PANIB_K1_WARP 0
+#endif
+#if PANIB_K1_WARP
+// ------------------------------------------------------------------------------------------------
+// Warp-private form (PANIB_K1_WARP, geometry compiled with PANIB_K1_THREADS = 32): every WARP is an
+// independent worker with its own 512-k-mer tiles, staging buffers, scratch and genome slot; the only CTA
+// barrier is the one at the end of the kernel.  The CTA form above synchronises its 8 warps twice per tile,
+// and ncu attributes 19 % of all warp samples to those two barriers (12.6 % top of the loop, 6.2 % between the
+// phases): the warps of a CTA do not finish a phase together -- the scheduler is not fair, survivors take the
+// rare path, one lane waits for the ticket atomic -- and every one of them waits for the slowest.
+// Work is handed out in units of kUnitTiles warp tiles (one ticket each).
+// ------------------------------------------------------------------------------------------------
+static_assert(kThreadsK1 == 32, "the warp-private kernel needs the 32-thread tile geometry");
+constexpr int kLaunchThreadsK1 = 256;
+constexpr int kWarpsK1 = kLaunchThreadsK1 / 32;
+constexpr int kUnitTiles = 2;  // warp tiles per ticket (divides kTileBases / kCtaTile: a unit lies in one genome)
+static_assert((kTileBases / kCtaTile) % kUnitTiles == 0, "unit geometry");
+
+template <int K>
+__global__ void __launch_bounds__(kLaunchThreadsK1, PANIB_K1_MINBLOCKS)
+sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                   const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
+                   const HashConsts hc, const int32_t *__restrict__ nb,
+                   const uint64_t *__restrict__ bmul, uint64_t *__restrict__ table, int64_t row_stride,
+                   int32_t *flags, int32_t *status, uint32_t *ticket, const SurvivorBuf surv) {
+    const uint64_t max_hash = hc.max_hash;
+    __shared__ __align__(16) uint32_t sp_all[kWarpsK1][2][kSpStage];
+    __shared__ __align__(16) uint32_t sm_all[kWarpsK1][2][kTileMaskWords];
+    __shared__ __align__(16) uint32_t rcp_all[kWarpsK1][kSpStage];
+    __shared__ GenomeSlot s_slot[kWarpsK1];
+    __shared__ int64_t s_range[kWarpsK1][2];  // stream tiles [lo, hi) of the genome in s_slot
+    __shared__ uint32_t s_nsurv;
+    extern __shared__ __align__(16) uint32_t scratch_all[];  // kK1DynSmem bytes: one block of 2 * kBlkPos * 32 words per warp
+    constexpr int S = kTileBases / kCtaTile;  // warp tiles per stream tile
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t *const scratch = scratch_all + w * (2 * kBlkPos * 32);
+    uint32_t(*const sp_)[kSpStage] = sp_all[w];
+    uint32_t(*const sm)[kTileMaskWords] = sm_all[w];
+    uint32_t *const rcp = rcp_all[w] + kSpLead;
+    if (threadIdx.x == 0) s_nsurv = 0u;
+    if (lane < 2 * kSpLead) sp_[lane / kSpLead][lane % kSpLead] = 0u;  // lead-in words: read, never used
+    else if (lane < 3 * kSpLead) rcp_all[w][lane - 2 * kSpLead] = 0u;
+    else if (lane < 3 * kSpLead + 2) s_range[w][lane - 3 * kSpLead] = 0;  // empty range: the first unit looks its genome up
+    __syncthreads();  // s_nsurv
+    const int64_t wt0 = tile_begin * S;                              // first warp tile of the launch
+    const int64_t units = (n_tiles - tile_begin) * (S / kUnitTiles);  // tickets in the launch
+    const int64_t n_workers = (int64_t)gridDim.x * kWarpsK1;
+    auto prefetch = [&](int64_t t, int b) {
+        const uint32_t *gp = packed + t * (kCtaTile / 16);
+        const uint32_t *gm = mask + t * (kCtaTile / 32);
+        if (lane < kTileWords / 4) cp_async16(sp_[b] + kSpLead + 4 * lane, gp + 4 * lane);
+        else if (lane < kTileWords / 4 + kTileMaskWords / 4)
+            cp_async16(sm[b] + 4 * (lane - kTileWords / 4), gm + 4 * (lane - kTileWords / 4));
+        cp_async_commit();
+    };
+    static_assert(kTileWords / 4 + kTileMaskWords / 4 <= 32, "one warp stages a tile with one cp.async per lane");
+    int64_t unit = (int64_t)blockIdx.x * kWarpsK1 + w;  // first unit: static; later ones from the ticket counter
+    int64_t next_unit = units;                          // known once sub-tile 0 of `unit` is done
+    int64_t wt = wt0 + unit * kUnitTiles;
+    int sub = 0;
+    if (unit < units) prefetch(wt, 0);
+    const int u = lane >> 2, a = lane & 3;
+    const EmitToTable emit{&s_slot[w], max_hash, status, surv, &s_nsurv};
+    int g = 0;
+    for (int it = 0; unit < units; ++it) {
+        const int cur = it & 1;
+        cp_async_wait<0>();
+        __syncwarp();  // tile `cur` has landed; every lane is done with the previous tile's scratch
+        const bool last_sub = sub == kUnitTiles - 1;
+        const int64_t following = last_sub ? wt0 + next_unit * kUnitTiles : wt + 1;
+        if (!last_sub || next_unit < units) prefetch(following, cur ^ 1);
+        const uint32_t *sp = sp_[cur] + kSpLead;
+        uint32_t drawn = 0;
+        if (sub == 0 && lane == 0) {  // once per unit: the next ticket, and this unit's genome
+            if (ticket) drawn = atomicAdd(ticket, 1u);
+            const int64_t st_tile = wt / S;
+            if (st_tile < s_range[w][0] || st_tile >= s_range[w][1]) {
+                g = find_genome(tile_off, n_genomes, st_tile, g);
+                s_slot[w] = GenomeSlot{table + (size_t)g * row_stride, __ldg(bmul + g), flags + g, __ldg(nb + g), g};
+                s_range[w][0] = __ldg(tile_off + g);
+                s_range[w][1] = __ldg(tile_off + g + 1);
+            }
+        }
+        // phase A: one item per lane, then the halo
+        tile_expand_item<K>(sp, rcp, scratch, 32, lane);
+        tile_expand_halo<K>(sp, rcp, scratch, 32, lane);
+        const uint32_t mw = lane < kTileMaskWords ? sm[cur][lane] : 0u;
+        const bool dirty = __any_sync(0xFFFFFFFFu, mw != 0u) != 0;
+        __syncwarp();
+        // phase B
+        const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
+        hash_thread_kmers<K>(sp, rcp, scratch + 2 * lane, u, a, vmask, hc, emit);
+        if (sub == 0) {
+            const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, drawn, 0);
+            next_unit = ticket ? n_workers + (int64_t)d0 : unit + n_workers;
+        }
+        if (last_sub) {
+            unit = next_unit;
+            wt = wt0 + unit * kUnitTiles;
+            sub = 0;
+        } else {
+            sub++;
+            wt++;
+        }
+    }
+    if (surv.cap) {
+        __syncthreads();
+        if (threadIdx.x == 0) surv.count[blockIdx.x] = s_nsurv < surv.cap ? s_nsurv : surv.cap;
+    }
+}
+#else
+constexpr int kLaunchThreadsK1 = kThreadsK1;
 template <int K>
 __global__ void __launch_bounds__(kThreadsK1, PANIB_K1_MINBLOCKS)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
@@ -173,6 +286,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     __shared__ __align__(16) uint32_t sm[2][kTileMaskWords];
     __shared__ __align__(16) uint32_t rcp_[kSpStage];
     __shared__ GenomeSlot s_slot;
+    __shared__ int64_t s_range[2];  // stream tiles [lo, hi) of the genome in s_slot
     __shared__ int64_t s_next;
     __shared__ uint32_t s_nsurv;
     // per-thread ASCII scratch as pairs of words (kmer_hash.cuh: scr_index)
@@ -197,6 +311,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     prefetch(tile, 0);
     if (tid < 2 * kSpLead) sp_[tid / kSpLead][tid % kSpLead] = 0u;  // lead-in words: read, never used
     else if (tid < 3 * kSpLead) rcp_[tid - 2 * kSpLead] = 0u;
+    else if (tid < 3 * kSpLead + 2) s_range[tid - 3 * kSpLead] = 0;  // empty: the first tile looks its genome up
     uint32_t *const rcp = rcp_ + kSpLead;
     // Tiles after a CTA's first come from a ticket counter (`ticket`, zeroed by the host before the
     // launch) rather than from a fixed stride: the warp scheduler favours some resident CTAs, so with
@@ -213,16 +328,24 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         const int cur = it & 1;
         cp_async_wait<0>();
         __syncthreads();  // tile `cur` has landed; every thread is done with the previous tile's scratch
+        if (it) next = s_next;  // drawn during the previous tile, stored after its phase B
         if (next < n_tiles) prefetch(next, cur ^ 1);
         const uint32_t *sp = sp_[cur] + kSpLead;
-        // one thread per job: next ticket (warp 0), this tile's genome slot (warp 1)
+        // One thread per job, and neither may hold its warp back before the barrier between the phases (the
+        // other seven would wait for it): the ticket of the tile after next is only ISSUED here, its value is
+        // stored after phase B; the genome slot changes once in ~20,000 CTA tiles, so the common case is a
+        // range test on two shared words instead of dependent global loads.
         uint32_t drawn = 0;
         if (tid == 0) {
             if (ticket && next < n_tiles) drawn = atomicAdd(ticket, 1u);
-            s_next = ticket ? (next < n_tiles ? dyn_base + drawn : n_tiles) : next + gridDim.x;
         } else if (tid == 32) {
-            g = find_genome(tile_off, n_genomes, tile / S, g);
-            s_slot = GenomeSlot{table + (size_t)g * row_stride, __ldg(bmul + g), flags + g, __ldg(nb + g), g};
+            const int64_t st_tile = tile / S;
+            if (st_tile < s_range[0] || st_tile >= s_range[1]) {
+                g = find_genome(tile_off, n_genomes, st_tile, g);
+                s_slot = GenomeSlot{table + (size_t)g * row_stride, __ldg(bmul + g), flags + g, __ldg(nb + g), g};
+                s_range[0] = __ldg(tile_off + g);
+                s_range[1] = __ldg(tile_off + g + 1);
+            }
         }
         // phase A: items 0..255 one per thread, the halo by warp 2
         tile_expand_item<K>(sp, rcp, scratch, kThreadsK1, tid);
@@ -232,14 +355,17 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         // phase B
         const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
         hash_thread_kmers<K>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, emit);
+        // read by everyone after the next barrier; the last read of the old value was before the barrier above
+        if (tid == 0) s_next = ticket ? (next < n_tiles ? dyn_base + drawn : n_tiles) : next + gridDim.x;
         tile = next;
-        next = s_next;  // written before the barrier above, overwritten after the next one
     }
     if (surv.cap) {
         __syncthreads();
         if (tid == 0) surv.count[blockIdx.x] = s_nsurv < surv.cap ? s_nsurv : surv.cap;
     }
 }
+
+#endif  // PANIB_K1_WARP
 
 // the parked survivors of a K1 launch -> their genomes' bucketed rows.  grid = (chunks of a region, CTAs of K1)
 __global__ void __launch_bounds__(256)
@@ -473,8 +599,14 @@ static dim3 tile_grid(int64_t n_tiles) {  // one CTA per tile (generic kernel); 
     return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
-constexpr size_t kK1DynSmem = 2 * kBlkPos * kThreadsK1 * sizeof(uint32_t);  // per-thread ASCII scratch
+constexpr size_t kK1DynSmem = 2 * kBlkPos * kLaunchThreadsK1 * sizeof(uint32_t);  // per-thread ASCII scratch
 
+// k-mer starts one CTA takes per round of tickets (CTA form: one CTA tile; warp form: one unit per warp)
+#if PANIB_K1_WARP
+constexpr int kLaunchTileK1 = kWarpsK1 * kUnitTiles * kCtaTile;
+#else
+constexpr int kLaunchTileK1 = kCtaTile;
+#endif
 // persistent grid of the fast kernel: SMs x resident CTAs per SM
 template <int K>
 static int persistent_grid(int64_t n_tiles) {
@@ -484,7 +616,7 @@ static int persistent_grid(int64_t n_tiles) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(sketch_hash_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1DynSmem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K>, kThreadsK1, kK1DynSmem) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K>, kLaunchThreadsK1, kK1DynSmem) !=
                 cudaSuccess || per_sm < 1)
             per_sm = 2;
         cached = sms * per_sm;
@@ -574,9 +706,9 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
     SurvivorBuf surv{nullptr, nullptr, nullptr, 0u};
     int ctas = 0;
 #define PANIB_LAUNCH_K(KK)                                                                                   \
-    ctas = persistent_grid<KK>(n * (kTileBases / kCtaTile));                                                 \
+    ctas = persistent_grid<KK>((n * (int64_t)kTileBases + kLaunchTileK1 - 1) / kLaunchTileK1);               \
     surv = survivor_regions(ctas, n * (int64_t)kTileBases, max_hash);                                    \
-    sketch_hash_kernel<KK><<<ctas, kThreadsK1, kK1DynSmem, st>>>(                                            \
+    sketch_hash_kernel<KK><<<ctas, kLaunchThreadsK1, kK1DynSmem, st>>>(                                         \
         d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, hc, d_nb, d_bmul,                \
         d_table, row_stride, d_flags, d_status, ticket, surv)
     switch (k) {

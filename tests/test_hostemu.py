@@ -10,6 +10,7 @@ specialised murmur) is proven bit-exact before GPU time is spent.  The GPU parit
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import numpy as np
@@ -23,7 +24,7 @@ from pyani_plus_b200 import stream
 @pytest.fixture(scope="module")
 def emu() -> ctypes.CDLL:
     entry.build()
-    lib = ctypes.CDLL(str(entry.PKG / "libpanib_hostemu.so"))
+    lib = ctypes.CDLL(os.environ.get("PANIB_HOSTEMU_LIB", str(entry.PKG / "libpanib_hostemu.so")))  # override: variant geometry
     lib.emu_sketch_tiles.restype = ctypes.c_int64
     lib.emu_sketch_tiles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p,
