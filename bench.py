@@ -10,9 +10,11 @@ sketches when N > 1], kernel K2 over every unordered genome pair, and the ANI ke
 
 * ``value``  whole-job genome pairs/s with the 2-bit packed genomes already resident in HBM.
 * ``e2e``    the same metric through the public engine API from HOST buffers: the ASCII genomes are packed
-             (2 bits + validity bit per base) by the library's host threads into pinned memory, copied
-             host->device chunk by chunk while K1 hashes the chunks already there, intersected, and the two
-             float64 ANI matrices are copied back -- all inside the timed region.
+             (2 bits per base; validity masks only for tiles that hold an invalid base) by the library's
+             host threads into pinned memory and copied host->device chunk by chunk, chunks from the tail of
+             the stream cross as plain ASCII while the link would otherwise idle and are packed on the GPU,
+             K1 hashes the chunks already there, K2 intersects, and the two float64 ANI matrices are copied
+             back -- all inside the timed region.
 * ``roofline``       dominant kernel of the step, algorithmic bytes / CUDA-event time vs measured HBM peak.
 * ``cpu_baseline``   the oracle (CPU port of the same algorithm) timed on the host cores (rank 0).
 
@@ -562,17 +564,47 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
                "note": "integer-ALU bound by construction (MurmurHash3 over 31 ASCII bytes per base); see "
                        "DESIGN.md and profiles/ for pipe utilisation",
                "integer_pipes": integer_pipe_view(local_bases, k1_hash_ms, dev_t["clocks"], cap_k1)}
-    roof_k2 = {"kernel": ("intersect_kernel (K2, probing form)" if stepper.k2_method == "probe" else
-                          "index_* kernels (K2, inverted-index form: sort + AND/POPC bit matrix + rare-pair adds)"), "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
-               "frac": k2_gbs / peak,
-               "traffic": (cap_k2 or {}).get("dram_bytes") if world == 1 else None,
-               "algorithmic_bytes": k2_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
-               "bytes_per_pair": k2_bytes * world / max(1, n_pairs),
-               "note": ("algorithmic bytes 8(|A|+|B|)+4 per pair; staged queries and L2-resident columns make "
-                        "DRAM traffic far smaller" if stepper.k2_method == "probe" else
-                        "algorithmic bytes keep SURVEY 8d's per-pair definition 8(|A|+|B|)+4, which the "
-                        "inverted-index form does not need to touch (it reads every sketch once, sorts the "
-                        "entries and works on shared hashes only), hence frac >> 1; its own cost is in stage_ms")}
+    if stepper.k2_method == "probe":
+        roof_k2 = {"kernel": "intersect_kernel (K2, probing form)", "bound": "hbm", "achieved": k2_gbs, "peak": peak,
+                   "unit": "GB/s", "frac": k2_gbs / peak,
+                   "traffic": (cap_k2 or {}).get("dram_bytes") if world == 1 else None,
+                   "algorithmic_bytes": k2_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
+                   "bytes_per_pair": k2_bytes * world / max(1, n_pairs),
+                   "note": "algorithmic bytes 8(|A|+|B|)+4 per pair (SURVEY 8d); staged queries and L2-resident "
+                           "columns make DRAM traffic far smaller, so frac can exceed 1"}
+    else:
+        # The inverted-index form never touches what SURVEY 8d's per-pair definition counts (it reads every sketch
+        # ONCE), so it gets the byte model of its own kernels: what each of them must move once, per rank.
+        est = eng.last_intersect_estimates or {}
+        own = tot_cnt if world == 1 else min(tot_cnt, 2 * (tot_cnt // world) + 4096)
+        slots = 1024
+        while slots < 2 * own:
+            slots <<= 1
+        cols = int(est.get("frequent_hashes", 0))
+        rare_pairs = int(est.get("rare_pairs", 0))
+        t64 = (n + 63) // 64
+        idx_bytes = (16.0 * slots                       # hash table cleared: key 8 + count 4 + aux 4 per slot
+                     + 8.0 * tot_cnt                    # insert: every rank reads every entry's hash
+                     + (20.0 + 12.0 + 16.0 + 16.0) * tot_cnt / world  # insert (slot CAS + count + tag write), classify,
+                                                                      # emit, sparse: tags / counts read per owned entry
+                     + 8.0 * rare_pairs                 # one 4-byte atomic read-modify-write per rare pair
+                     + t64 * (t64 + 1) / 2 * 2 * 64 * ((cols + 31) // 32) * 4.0  # bit-matrix rows per 64x64 tile
+                     + 8.0 * n * n)                     # mirror: count matrix read and written
+        idx_gbs = idx_bytes / (k2_ms * 1e-3) / 1e9
+        roof_k2 = {"kernel": "index_* kernels (K2, inverted-index form: hash-table group-by + AND/POPC bit matrix "
+                             "+ rare-pair adds)", "bound": "hbm", "achieved": idx_gbs, "peak": peak, "unit": "GB/s",
+                   "frac": idx_gbs / peak,
+                   "traffic": (cap_k2 or {}).get("dram_bytes") if world == 1 else None,
+                   "algorithmic_bytes": idx_bytes, "peak_source": peak_src, "ms_per_launch": k2_ms,
+                   "bytes_per_pair": idx_bytes * world / max(1, n_pairs),
+                   "per_pair_definition": {"algorithmic_bytes": k2_bytes, "achieved": k2_gbs, "frac": k2_gbs / peak},
+                   "model": {"table_slots": slots, "entries": tot_cnt, "bit_matrix_columns": cols,
+                             "rare_pairs": rare_pairs},
+                   "note": "byte model of the form's own kernels (DESIGN.md 4): table clear 16 B/slot, 8 B/entry read "
+                           "by every rank, 64 B/owned entry of slot / tag / list accesses over insert, classify, emit "
+                           "and sparse, 8 B per rare pair, bit-matrix rows per 64x64 tile, N^2 x 8 B mirror; "
+                           "per_pair_definition keeps SURVEY 8d's 8(|A|+|B|)+4, which this form does not move "
+                           "(frac >> 1 there)"}
     # the CPU leg runs at N=1 only (under torchrun the workers are pinned to one OpenMP thread)
     cpu = cpu_measure(args.workload, 2, 1) if (world == 1 and not args.no_cpu_baseline) else None
     line = {

@@ -54,18 +54,29 @@ def summarise(rep: Path) -> dict:
     rows = raw_rows(rep)
     un = units(rep)
     out = {"launches": len(rows), "kernels": sorted({r.get("Kernel Name", "?")[:80] for r in rows})}
-    tot = {"dram_bytes": 0.0, "inst_executed": 0.0, "duration_ms": 0.0}
+    # one logical call = one launch of every distinct kernel in the report: average the launches of a kernel
+    # (a capture window may hold several calls), then sum over the kernels
+    per_kernel: dict[str, dict[str, list[float]]] = {}
     for r in rows:
-        for key, name in (("dram__bytes_read.sum", "dram_bytes"), ("dram__bytes_write.sum", "dram_bytes")):
+        acc = per_kernel.setdefault(r.get("Kernel Name", "?"), {"dram_bytes": [], "inst_executed": [], "duration_ms": []})
+        dram = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             v = f(r, key)
             if v is not None:
-                tot[name] += v * SCALE.get(un.get(key, "byte"), 1.0)
+                dram += v * SCALE.get(un.get(key, "byte"), 1.0)
+        acc["dram_bytes"].append(dram)
         v = f(r, "smsp__inst_executed.sum")
         if v is not None:
-            tot["inst_executed"] += v
+            acc["inst_executed"].append(v)
         v = f(r, "gpu__time_duration.sum")
         if v is not None:
-            tot["duration_ms"] += v * SCALE.get(un.get("gpu__time_duration.sum", "ms"), 1.0)
+            acc["duration_ms"].append(v * SCALE.get(un.get("gpu__time_duration.sum", "ms"), 1.0))
+    tot = {name: sum(sum(a[name]) / len(a[name]) for a in per_kernel.values() if a[name])
+           for name in ("dram_bytes", "inst_executed", "duration_ms")}
+    out["per_kernel"] = {k[:60]: {"launches_in_report": len(a["duration_ms"]),
+                                  "duration_ms": sum(a["duration_ms"]) / max(1, len(a["duration_ms"])),
+                                  "dram_bytes": sum(a["dram_bytes"]) / max(1, len(a["dram_bytes"]))}
+                         for k, a in per_kernel.items()}
     out.update(tot)
     big = max(rows, key=lambda r: f(r, "gpu__time_duration.sum") or 0.0)
     out["pipe_busy"] = {

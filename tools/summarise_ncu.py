@@ -114,10 +114,14 @@ def main() -> None:
         (PROF / f"{tag}_launches_k2_index.md").write_text(
             "`python tools/time_k1.py config3 1`: K1, the probing K2 and the inverted-index K2 (CUB radix sort + "
             "scan + `index_*` kernels) on 1,000 genomes\n\n" + summarise_launches(launches_idx))
-    for kind, title in (("k1", "K1 sketch_hash_kernel (config 2: 100 x 5 Mb)"),
+    r1 = tag == "r01"  # round 1 profiled configs[1] (100 genomes); later rounds the bench default, configs[2]
+    for kind, title in (("k1", "K1 sketch_hash_kernel (configs[1]: 100 x 5 Mb)" if r1 else
+                         "K1 sketch_hash_kernel<31> (configs[2]: 1,000 x 5 Mb, one launch = 5 Gbp)"),
                         ("k2", "K2 intersect_kernel (config 2: 4,950 pairs)"),
                         ("k2c3", "K2 intersect_kernel (config 3: 1,000 genomes, 499,500 pairs)"),
-                        ("k2idx", "K2 index_dense_kernel, AND+POPC over the bit matrix (config 3: 1,000 genomes)")):
+                        ("k2probe", "K2 intersect_kernel, probing form (configs[2]: 1,000 genomes, 499,500 pairs)"),
+                        ("k2idx", "K2 index_dense_kernel, AND+POPC over the bit matrix (config 3: 1,000 genomes)" if r1
+                         else "K2 inverted-index form, every kernel of its steps (configs[2]: 1,000 genomes)")):
         rep = OUT / f"prof_{kind}_{tag}.ncu-rep"
         if rep.is_file():
             (PROF / f"{tag}_{kind}_ncu.md").write_text(summarise_report(rep, title) + "\n")
