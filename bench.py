@@ -382,7 +382,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
     # with the all-gather through peer-mapped memory (an error if that cannot be set up, unless --nccl-gather)
     stepper, exchange = run_mod.make_step(
         eng, plan, bufs, tab, k, ctx, h_ascii=h_ascii, k2_method=args.k2, nccl_gather=args.nccl_gather,
-        host_threads=max(1, len(os.sched_getaffinity(0)) // max(1, world)))
+        host_threads=args.host_threads or max(1, len(os.sched_getaffinity(0)) // max(1, world)))
     size_hint = stepper.size_hint
     # the step as ONE CUDA graph launch (all ranks must agree, the gather has barriers inside)
     graphed: dict = {}
@@ -672,6 +672,8 @@ def main() -> None:
                          "timed every step when it fits, else a bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=0,
+                    help="host threads per rank that pack ASCII in the e2e step (default: the rank's share of the cores)")
     ap.add_argument("--k2", default="auto", choices=["auto", "probe", "index"],
                     help="pairwise kernel: probing form, inverted-index form, or chosen from the data")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA graph replay)")

@@ -98,6 +98,11 @@ CREATE TABLE IF NOT EXISTS runs_genomes (
 );
 """
 
+# The reference caches each N x N matrix of a run as ONE JSON text in the runs table (db_orm.py:393-466); SQLite's
+# SQLITE_MAX_LENGTH is 10^9 bytes, a float cell is ~20 bytes of JSON: runs above ~7,000 genomes are not cached.
+MATRIX_CACHE_MAX_BYTES = 900_000_000
+MATRIX_JSON_BYTES_PER_CELL = 20
+
 COMPARISON_COLUMNS = (
     "query_hash", "subject_hash", "configuration_id", "identity", "aln_length", "sim_errors",
     "cov_query", "cov_subject", "uname_system", "uname_release", "uname_machine",
@@ -415,6 +420,13 @@ class Run:
         hashes = sorted(a.genome_hash for a in self.fasta_hashes)
         where = {h: i for i, h in enumerate(hashes)}
         size = len(hashes)
+        if size * size * MATRIX_JSON_BYTES_PER_CELL > MATRIX_CACHE_MAX_BYTES:
+            # SQLite refuses strings above 10^9 bytes (SQLITE_MAX_LENGTH), and the reference's cache format is
+            # one JSON text per matrix: beyond ~7,000 genomes it cannot be stored.  The run stays complete -- the
+            # comparisons table holds every value -- and the matrix properties below rebuild from it on demand.
+            self.df_identity = self.df_cov_query = self.df_hadamard = None
+            self.df_aln_length = self.df_sim_errors = None
+            return
         identity = np.full([size, size], np.nan, float)
         cov_query = np.full([size, size], np.nan, float)
         aln_length = np.full([size, size], np.nan, float)
@@ -444,34 +456,63 @@ class Run:
         self.df_aln_length = as_json(aln_length)
         self.df_sim_errors = as_json(sim_errors)
 
-    def _matrix(self, text: str | None, *, as_float: bool) -> "DataFrame | None":  # noqa: UP037
+    def _matrix(self, text: str | None, *, as_float: bool, column: str | None = None) -> "DataFrame | None":  # noqa: UP037
         if not text:
-            return None
+            return self._matrix_from_comparisons(column) if column else None
         import pandas as pd  # noqa: PLC0415
 
         if as_float:
             return pd.read_json(StringIO(text), orient="split", dtype=float)
         return pd.read_json(StringIO(text), orient="split")
 
+    def _matrix_from_comparisons(self, column: str) -> "DataFrame | None":  # noqa: UP037
+        """A matrix of a COMPLETE run too large for the JSON cache (see ``cache_comparisons``), read from the
+        comparisons table; None for a run that is not complete (what an empty cache means in the reference)."""
+        import numpy as np  # noqa: PLC0415
+        import pandas as pd  # noqa: PLC0415
+
+        if self._session is None or self.status != "Done":
+            return None
+        hashes = sorted(a.genome_hash for a in self.fasta_hashes)
+        size = len(hashes)
+        if size * size * MATRIX_JSON_BYTES_PER_CELL <= MATRIX_CACHE_MAX_BYTES:
+            return None
+        where = {h: i for i, h in enumerate(hashes)}
+        cols = ("identity", "cov_query") if column == "hadamard" else (column,)
+        out = [np.full([size, size], np.nan, float) for _ in cols]
+        sql = ("SELECT comparisons.query_hash, comparisons.subject_hash, "
+               + ", ".join(f"comparisons.{c}" for c in cols) + _RUN_JOIN)
+        seen = 0
+        for q, s, *vals in self._session.execute(sql, (self.configuration_id, self.run_id, self.run_id)):
+            row, col = where[q], where[s]
+            for m, v in zip(out, vals, strict=True):
+                if v is not None:
+                    m[row, col] = v
+            seen += 1
+        if seen != size * size:
+            return None
+        data = out[0] * out[1] if column == "hadamard" else out[0]
+        return pd.DataFrame(data=data, index=hashes, columns=hashes, dtype=float)
+
     @property
     def identities(self) -> "DataFrame | None":  # noqa: UP037
-        return self._matrix(self.df_identity, as_float=True)
+        return self._matrix(self.df_identity, as_float=True, column="identity")
 
     @property
     def cov_query(self) -> "DataFrame | None":  # noqa: UP037
-        return self._matrix(self.df_cov_query, as_float=True)
+        return self._matrix(self.df_cov_query, as_float=True, column="cov_query")
 
     @property
     def aln_length(self) -> "DataFrame | None":  # noqa: UP037
-        return self._matrix(self.df_aln_length, as_float=False)
+        return self._matrix(self.df_aln_length, as_float=False, column="aln_length")
 
     @property
     def sim_errors(self) -> "DataFrame | None":  # noqa: UP037
-        return self._matrix(self.df_sim_errors, as_float=False)
+        return self._matrix(self.df_sim_errors, as_float=False, column="sim_errors")
 
     @property
     def hadamard(self) -> "DataFrame | None":  # noqa: UP037
-        return self._matrix(self.df_hadamard, as_float=True)
+        return self._matrix(self.df_hadamard, as_float=True, column="hadamard")
 
     @property
     def tani(self) -> "DataFrame | None":  # noqa: UP037

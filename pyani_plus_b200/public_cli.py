@@ -196,6 +196,10 @@ def run_method(  # noqa: PLR0913, PLR0917
             log_sys_exit(logger, msg)  # pragma: no cover
         if run_.df_identity is None or done:
             run_.cache_comparisons()
+        if run_.df_identity is None:
+            msg = (f"The {n}x{n} matrices are too large for the database's JSON cache (SQLite stores at most 10^9 "
+                   "bytes per text); they will be read from the comparisons table when needed")
+            logger.warning(msg)
         run_.status = "Done"
         session_.commit()
         msg = f"Completed {method} run-id {run_id} with {n} genomes in database {database}"

@@ -383,3 +383,44 @@ def test_c_fasta_parser_matches_python_iterator(golden: Path, tmp_path: Path) ->
         assert title == (records[0][0] if records else None)
     stream, n, total, title = engine.fasta_to_stream(b"")
     assert (stream.size, n, total, title) == (0, 0, 0, None)
+
+
+def test_matrix_cache_skipped_when_too_large_for_sqlite(tmp_path: Path, monkeypatch: pytest.MonkeyPatch) -> None:
+    """The reference caches every run matrix as ONE JSON text (db_orm.py:393-466); SQLite takes at most 10^9
+    bytes per text, so very large runs skip the cache and the matrix properties rebuild from the comparisons
+    table -- same values as the cached form."""
+    import logging
+
+    import numpy as np
+
+    from pyani_plus_b200 import db_orm
+
+    logger = logging.getLogger("test")
+    db = tmp_path / "big.sqlite"
+    hashes = [f"{i:032x}" for i in range(4)]
+    rng = np.random.default_rng(3)
+    ident = rng.random((4, 4))
+    cov = rng.random((4, 4))
+    ident[1, 2] = cov[1, 2] = np.nan
+    frames = {}
+    for limit in (db_orm.MATRIX_CACHE_MAX_BYTES, 100):  # second pass: 4 x 4 x 20 bytes is already "too large"
+        monkeypatch.setattr(db_orm, "MATRIX_CACHE_MAX_BYTES", limit)
+        with db_orm.connect_to_db(logger, db if limit > 100 else tmp_path / "big2.sqlite") as session:
+            config = db_orm.db_configuration(session, "sourmash", "panib200", "0", kmersize=31, extra="scaled=1000",
+                                             create=True)
+            for h in hashes:
+                db_orm.db_genome(logger, session, tmp_path / f"{h}.fna", h, create=True, stats=(10, b"t", False))
+            run = db_orm.add_run(session, config, "x", tmp_path, "Running", "t", None,
+                                 {tmp_path / f"{h}.fna": h for h in hashes})
+            assert db_orm.insert_comparison_arrays(logger, session, config.configuration_id, hashes, hashes, ident, cov)
+            run.cache_comparisons()
+            run.status = "Done"
+            session.commit()
+            assert (run.df_identity is None) == (limit == 100)
+            frames[limit] = (run.identities, run.cov_query, run.hadamard)
+            assert run.aln_length is not None or limit == 100
+    for a, b in zip(frames[100], frames[max(frames)], strict=True):
+        assert a is not None and b is not None
+        # the JSON cache keeps 10 significant digits (pandas' to_json, as in the reference); the table is exact
+        np.testing.assert_allclose(a.to_numpy(), b.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+        assert list(a.index) == list(b.index) == hashes
