@@ -231,15 +231,22 @@ PANIB_HD U64 fmix_head(U64 k) {  // fmix64 without its last xorshift
 
 template <int K>
 PANIB_HD Partial murmur_words(const uint32_t *W, const HashConsts &hc) {
+#if defined(PANIB_K1_SEED42)  // experiment: the seed-dependent constants as immediates instead of uniform registers
+    constexpr uint64_t kA1 = 42ull + 0x52dce729ull * kInv5, kA2 = 0x38495ab5ull * kInv5;
+    const U64 a1{(uint32_t)kA1, (uint32_t)(kA1 >> 32)}, a2{(uint32_t)kA2, (uint32_t)(kA2 >> 32)};
+    U64 h1{42u, 0u}, h2{42u, 0u};
+#else
+    const U64 a1 = hc.a1, a2 = hc.a2;
     U64 h1{hc.seed, 0u}, h2{hc.seed, 0u};
+#endif
     constexpr int nblocks = K / 16;
 #pragma unroll
     for (int i = 0; i < nblocks; i++) {
         h1 = xor64(h1, mix_k1(U64{W[4 * i], W[4 * i + 1]}));
-        if (i == 0) h1 = times5_sum(rotl<27>(h1), hc.a1);  // h2 is still the seed
+        if (i == 0) h1 = times5_sum(rotl<27>(h1), a1);  // h2 is still the seed
         else h1 = mul5_add<0x52dce729u>(add64(rotl<27>(h1), h2));
         h2 = xor64(h2, mix_k2(U64{W[4 * i + 2], W[4 * i + 3]}));
-        h2 = times5_sum(rotl<31>(h2), h1, hc.a2);
+        h2 = times5_sum(rotl<31>(h2), h1, a2);
     }
     constexpr int tail = K & 15;
     constexpr int tb = 4 * nblocks;  // first tail word
@@ -615,6 +622,21 @@ struct KmerStep {
 #if PANIB_K1_GROUP == 2
             const Partial p1 = KmerStep<K, J + 1, Emit>::hash_one(X, Xr, fw, hc);
 #endif
+#if defined(PANIB_K1_VOTE) && defined(__CUDA_ARCH__)
+            // experiment: one warp-uniform branch (vote) around the rare path instead of a divergent one
+#if PANIB_K1_GROUP == 2
+            const bool f0 = p0.prefilter(hc), f1 = p1.prefilter(hc);
+            if (__any_sync(0xFFFFFFFFu, f0 | f1)) {
+                if (f0 && (vmask & (1u << J))) emit(p0);
+                if (f1 && (vmask & (2u << J))) emit(p1);
+            }
+#else
+            const bool f0 = p0.prefilter(hc);
+            if (__any_sync(0xFFFFFFFFu, f0)) {
+                if (f0 && (vmask & (1u << J))) emit(p0);
+            }
+#endif
+#else
             if (p0.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
                 if (vmask & (1u << J)) emit(p0);
             }
@@ -622,6 +644,7 @@ struct KmerStep {
             if (p1.prefilter(hc)) {
                 if (vmask & (2u << J)) emit(p1);
             }
+#endif
 #endif
             KmerStep<K, J + PANIB_K1_GROUP, Emit>::run(X, Xr, fw, vmask, hc, emit);
         }
