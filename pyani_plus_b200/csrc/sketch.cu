@@ -177,7 +177,7 @@ constexpr int kWarpsK1 = kLaunchThreadsK1 / 32;
 constexpr int kUnitTiles = 2;  // warp tiles per ticket (divides kTileBases / kCtaTile: a unit lies in one genome)
 static_assert((kTileBases / kCtaTile) % kUnitTiles == 0, "unit geometry");
 
-template <int K>
+template <int K, bool S42>
 __global__ void __launch_bounds__(kLaunchThreadsK1, PANIB_K1_MINBLOCKS)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
                    const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
@@ -250,7 +250,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         __syncwarp();
         // phase B
         const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
-        hash_thread_kmers<K>(sp, rcp, scratch + 2 * lane, u, a, vmask, hc, emit);
+        hash_thread_kmers<K, S42>(sp, rcp, scratch + 2 * lane, u, a, vmask, hc, emit);
         if (sub == 0) {
             const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, drawn, 0);
             next_unit = ticket ? n_workers + (int64_t)d0 : unit + n_workers;
@@ -271,7 +271,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
 }
 #else
 constexpr int kLaunchThreadsK1 = kThreadsK1;
-template <int K>
+template <int K, bool S42>
 __global__ void __launch_bounds__(kThreadsK1, PANIB_K1_MINBLOCKS)
 sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
                    const int64_t *__restrict__ tile_off, int n_genomes, int64_t tile_begin, int64_t n_tiles,
@@ -354,7 +354,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         const bool dirty = __syncthreads_or(mw != 0u) != 0;
         // phase B
         const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
-        hash_thread_kmers<K>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, emit);
+        hash_thread_kmers<K, S42>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, emit);
         // read by everyone after the next barrier; the last read of the old value was before the barrier above
         if (tid == 0) s_next = ticket ? (next < n_tiles ? dyn_base + drawn : n_tiles) : next + gridDim.x;
         tile = next;
@@ -608,15 +608,15 @@ constexpr int kLaunchTileK1 = kWarpsK1 * kUnitTiles * kCtaTile;
 constexpr int kLaunchTileK1 = kCtaTile;
 #endif
 // persistent grid of the fast kernel: SMs x resident CTAs per SM
-template <int K>
+template <int K, bool S42>
 static int persistent_grid(int64_t n_tiles) {
     static int cached = 0;
     if (!cached) {
         int dev = 0, sms = 148, per_sm = 2;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(sketch_hash_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1DynSmem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K>, kLaunchThreadsK1, kK1DynSmem) !=
+        cudaFuncSetAttribute(sketch_hash_kernel<K, S42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1DynSmem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_hash_kernel<K, S42>, kLaunchThreadsK1, kK1DynSmem) !=
                 cudaSuccess || per_sm < 1)
             per_sm = 2;
         cached = sms * per_sm;
@@ -705,12 +705,15 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
     const HashConsts hc = make_hash_consts(seed, max_hash);
     SurvivorBuf surv{nullptr, nullptr, nullptr, 0u};
     int ctas = 0;
-#define PANIB_LAUNCH_K(KK)                                                                                   \
-    ctas = persistent_grid<KK>((n * (int64_t)kTileBases + kLaunchTileK1 - 1) / kLaunchTileK1);               \
-    surv = survivor_regions(ctas, n * (int64_t)kTileBases, max_hash);                                    \
-    sketch_hash_kernel<KK><<<ctas, kLaunchThreadsK1, kK1DynSmem, st>>>(                                         \
+#define PANIB_LAUNCH_KS(KK, SS)                                                                              \
+    ctas = persistent_grid<KK, SS>((n * (int64_t)kTileBases + kLaunchTileK1 - 1) / kLaunchTileK1);           \
+    surv = survivor_regions(ctas, n * (int64_t)kTileBases, max_hash);                                        \
+    sketch_hash_kernel<KK, SS><<<ctas, kLaunchThreadsK1, kK1DynSmem, st>>>(                                  \
         d_packed, d_mask, d_tile_off, (int)n_genomes, tile_begin, tile_end, hc, d_nb, d_bmul,                \
         d_table, row_stride, d_flags, d_status, ticket, surv)
+    // sourmash's seed (42) gets the instantiation with the seed-dependent constants as immediates
+#define PANIB_LAUNCH_K(KK)                                                                                   \
+    if (seed == kSourmashSeed) { PANIB_LAUNCH_KS(KK, true); } else { PANIB_LAUNCH_KS(KK, false); }
     switch (k) {
     case 21: PANIB_LAUNCH_K(21); break;
     case 31: PANIB_LAUNCH_K(31); break;
@@ -719,6 +722,7 @@ static int launch_hash_range(const uint32_t *d_packed, const uint32_t *d_mask, c
                                                                   tile_begin, tile_end, k, seed, max_hash, d_nb,
                                                                   d_bmul, d_table, row_stride, d_flags, d_status);
     }
+#undef PANIB_LAUNCH_KS
 #undef PANIB_LAUNCH_K
     int rc = check_launch("sketch_hash_kernel");
     if (rc || !surv.cap) return rc;

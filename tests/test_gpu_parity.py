@@ -555,3 +555,14 @@ def test_ingest_pipeline_paths_agree(eng, monkeypatch: pytest.MonkeyPatch) -> No
     run(h_pinned)
     bufs["ingest_scratch"] = scratch[: scratch.numel() // 8]  # room for the mask ring only
     run(h_pinned, PANIB_INGEST_RAW="2")
+
+
+@pytest.mark.parametrize("k", [21, 31])
+def test_other_seeds_take_the_general_instantiation(eng, k: int) -> None:
+    """The fast K1 kernels exist twice: seed 42 (sourmash's; constants as immediates) and any other seed
+    (constants in uniform registers).  Both equal the oracle."""
+    genomes = [[oracle.synth_genome(SEED, 900 + g, 150_000 + 4096 * g)] for g in range(3)]
+    for seed in (42, 7, 0xFFFFFFFF):
+        got = eng.sketch_genomes(genomes, k, 50, seed=seed).to_host()
+        for g, recs in enumerate(genomes):
+            assert got[g].tolist() == oracle.sketch_records(recs, k, 50, seed).tolist(), (seed, g)

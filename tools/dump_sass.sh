@@ -4,7 +4,7 @@
 TAG=${1:-r02}
 LIB=pyani_plus_b200/libpanib200.so
 mkdir -p profiles/$TAG
-for k in sketch_hash_kernelILi31 intersect_kernelILb0 index_insert_kernel index_classify_kernel index_dense_kernel \
+for k in sketch_hash_kernelILi31ELb1 intersect_kernelILb0 index_insert_kernel index_classify_kernel index_dense_kernel \
          index_sparse_kernel sketch_compact_scatter_kernel sketch_sort_buckets_kernel; do
   sym=$(cuobjdump -sass $LIB | grep "Function :" | grep "$k" | head -1 | awk '{print $3}')
   [ -z "$sym" ] && continue
