@@ -451,10 +451,11 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         wall = time.perf_counter() - wall0
         clocks = sampler.stop() if rank == 0 else None
         launches = eng.launch_count() - launches0 + (steps * per_step_launches[from_host] if graph else 0)
-        ing = eng.ingest_last() if from_host else {"h2d_bytes": 0, "chunks": 0, "chunks_as_ascii": 0, "dirty_tiles": 0}
+        ing = eng.ingest_last() if from_host else {"h2d_bytes": 0, "chunks": 0, "chunks_as_ascii": 0, "dirty_tiles": 0,
+                                                   "ring_bytes": 0}
         stats = torch.tensor([sum(tot), sum(t_k1), sum(t_gather), sum(t_k2), float(launches),
                               float(ing["h2d_bytes"]), float(ing["chunks"]), float(ing["chunks_as_ascii"]),
-                              float(ing["dirty_tiles"])], dtype=torch.float64, device=dev)
+                              float(ing["dirty_tiles"]), float(ing["ring_bytes"] > 0)], dtype=torch.float64, device=dev)
         if world > 1:
             mx = stats.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -465,7 +466,7 @@ def run_gpu(args: argparse.Namespace) -> None:  # noqa: PLR0915
         return {"ms": s[0] / steps, "k1_ms": s[1] / steps, "gather_ms": s[2] / steps, "k2_ms": s[3] / steps,
                 "launches": int(s[4]), "wall_s": wall, "clocks": clocks,
                 "ingest": {"h2d_bytes": int(s[5]), "chunks": int(s[6]), "chunks_as_ascii": int(s[7]),
-                           "dirty_tiles": int(s[8])}}
+                           "dirty_tiles": int(s[8]), "ranks_using_the_cached_ring": int(s[9])}}
 
     eager_t = timed_loop(False, args.steps, args.warmup)  # stage breakdown (events between the stages)
     dev_t = timed_loop(False, args.steps, args.warmup, graph=True) if graphed.get(False) else eager_t

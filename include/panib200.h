@@ -185,13 +185,19 @@ PANIB_API int panib_pack_host_tiles(const uint8_t *h_ascii, int64_t n_bases, uin
  *   - with room for at least one more chunk of ASCII, and h_ascii page-locked, chunks are also taken from the
  *     END of the stream as plain ASCII whenever the link would otherwise wait for the host threads, and packed
  *     on the GPU: host cores and link both stay busy whatever their relative speeds.
+ * The host threads write the packed words either to their place in h_packed (streaming stores; the DMA engine
+ * reads them back from DRAM) or through a 16 MB ring at the start of h_packed that stays in the last-level cache
+ * (no DRAM traffic for the packed form at all).  Which is faster depends on the host, so per calling thread and
+ * stream size the first call warms up, the second and third time one form each, and later calls use the faster;
+ * PANIB_INGEST_RING_MB=0 / N pins the choice.
  * d_counts == NULL skips the finalize step (rows stay bucketed hash sets, as after panib_sketch_hash_only).
  * The call returns when all host work is done and all device work is enqueued on `stream`.  The sketches do
  * not depend on which way a chunk travelled. */
 PANIB_API int64_t panib_ingest_scratch_bytes(int64_t n_bases);
-/* What the calling thread's last panib_sketch_packed_host moved: out4 = {bytes copied host->device, chunks,
- * chunks that travelled as ASCII, tiles whose mask was sent}. */
-PANIB_API int panib_ingest_last(int64_t *out4);
+/* What the calling thread's last panib_sketch_packed_host moved: out6 = {bytes copied host->device, chunks,
+ * chunks that travelled as ASCII, tiles whose mask was sent, bytes of the packed-word ring it used (0 = the
+ * whole-stream buffer), 1 if the call was one of the two that time the two forms against each other}. */
+PANIB_API int panib_ingest_last(int64_t *out6);
 PANIB_API int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_packed, uint32_t *h_mask, int64_t n_bases,
                              uint8_t *d_scratch, int64_t scratch_bytes,
                              uint32_t *d_packed, uint32_t *d_mask, const int64_t *d_tile_off,

@@ -90,14 +90,15 @@ __attribute__((target("avx2"))) static void pack_block_avx2(const uint8_t *a, in
 // it should neither be read for ownership nor stay in cache (the CALLER fences: pack_fence()).  One core's
 // demand misses do not saturate DRAM, so the ASCII stream is prefetched 4 KB ahead (measured on a Sapphire
 // Rapids host, 8 threads: 32 -> 49 GB/s of ASCII with the stores and the prefetch together).
-__attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_block_avx512(const uint8_t *a, int64_t n_groups,
-                                                                                   uint32_t *packed, uint32_t *mask) {
+template <bool kStream>
+__attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_block_avx512_t(const uint8_t *a, int64_t n_groups,
+                                                                                     uint32_t *packed, uint32_t *mask) {
     const __m512i up = _mm512_set1_epi8((char)0xDF);
     const __m512i lut_code = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 0, 0, 1, 3, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0));
     const __m512i lut_chr = _mm512_broadcast_i32x4(
         _mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1));
     const __m512i w14 = _mm512_set1_epi16(0x0401), w116 = _mm512_set1_epi32(0x00100001);
-    const bool nt = ((uintptr_t)packed & 63) == 0;
+    const bool nt = kStream && ((uintptr_t)packed & 63) == 0;
     int64_t g = 0;
     for (; g + 8 <= n_groups; g += 8) {
         __m128i q[4];
@@ -127,11 +128,21 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_block_avx5
     }
     if (g < n_groups) pack_block_scalar(a + 32 * g, n_groups - g, packed + 2 * g, mask + g);
 }
+// streaming form: for a destination that is written once and read by the DMA engine much later (a whole-stream
+// buffer); cached form: for a small ring that is re-used while it is still in the last-level cache, so that
+// neither the stores nor the DMA reads go to DRAM
+static void pack_block_avx512(const uint8_t *a, int64_t n_groups, uint32_t *packed, uint32_t *mask) {
+    pack_block_avx512_t<true>(a, n_groups, packed, mask);
+}
+static void pack_block_avx512_cached(const uint8_t *a, int64_t n_groups, uint32_t *packed, uint32_t *mask) {
+    pack_block_avx512_t<false>(a, n_groups, packed, mask);
+}
 // non-temporal stores are weakly ordered: fence before the packed words are handed to another thread / the DMA engine
 static inline void pack_fence() { _mm_sfence(); }
 
+
 using PackFn = void (*)(const uint8_t *, int64_t, uint32_t *, uint32_t *);
-static PackFn choose_pack(int force) {
+static PackFn choose_pack(int force, bool cached = false) {
     // force: 0 = best available, 1 = scalar, 2 = AVX2, 3 = AVX-512 (tests); unavailable -> nullptr
     __builtin_cpu_init();
     if (force == 0) {  // PANIB_PACK_ISA=scalar|avx2|avx512 pins the pool's code path (diagnostics)
@@ -145,7 +156,7 @@ static PackFn choose_pack(int force) {
     case 1: return pack_block_scalar;
     case 2: return has2 ? pack_block_avx2 : nullptr;
     case 3: return has512 ? pack_block_avx512 : nullptr;
-    default: return has512 ? pack_block_avx512 : has2 ? pack_block_avx2 : pack_block_scalar;
+    default: return has512 ? (cached ? pack_block_avx512_cached : pack_block_avx512) : has2 ? pack_block_avx2 : pack_block_scalar;
     }
 }
 
@@ -170,6 +181,12 @@ public:
         uint8_t *tile_dirty = nullptr;  // [tiles]: 1 = the tile holds an invalid base and its 128 mask words were written
         int64_t blocks_per_chunk = 0;   // > 0: chunk_state[] decides who handles a chunk
         std::vector<std::atomic<uint8_t>> chunk_state;  // 0 free, 1 being packed by the pool, 2 taken raw by the submitter
+        // packed output as a RING of ring_blocks blocks (0 = the whole stream, block b at its own offset): block b may
+        // be written once every block < b - ring_blocks + 1 has been copied away, which the submitter reports in
+        // free_upto (blocks < free_upto are free again)
+        int64_t ring_blocks = 0;
+        std::atomic<int64_t> free_upto{0};
+        std::atomic<bool> abort{false};
         std::atomic<int64_t> next{0}, finished{0};
         std::vector<std::atomic<uint8_t>> done;
         Job(int64_t blocks, int64_t chunks) : chunk_state((size_t)chunks), done((size_t)blocks) {
@@ -186,16 +203,24 @@ public:
                 if (cur == 0 && st.compare_exchange_strong(cur, 1, std::memory_order_acq_rel)) cur = 1;
                 skip = cur == 2;
             }
+            if (!skip && ring_blocks > 0) {  // wait for the ring slot (never on the submitting thread: it frees them)
+                while (b >= free_upto.load(std::memory_order_acquire) + ring_blocks) {
+                    if (abort.load(std::memory_order_relaxed)) { skip = true; break; }
+                    _mm_pause();
+                }
+            }
             if (!skip) {
                 const int64_t g0 = b * groups_per_block;
                 const int64_t ng = g0 + groups_per_block <= n_groups ? groups_per_block : n_groups - g0;
+                // where the packed words of group g go: their own offset, or the block's slot of the ring
+                uint32_t *const pk = ring_blocks > 0 ? packed + 2 * ((b % ring_blocks) * groups_per_block - g0) : packed;
                 if (!tile_dirty) {
-                    fn(ascii + 32 * g0, ng, packed + 2 * g0, mask + g0);
+                    fn(ascii + 32 * g0, ng, pk + 2 * g0, mask + g0);
                 } else {  // tile by tile: the mask of a clean tile is never written
                     constexpr int64_t kTileGroups = PANIB_TILE_BASES / 32;
                     alignas(64) uint32_t local[kTileGroups];
                     for (int64_t g = g0; g < g0 + ng; g += kTileGroups) {
-                        fn(ascii + 32 * g, kTileGroups, packed + 2 * g, local);
+                        fn(ascii + 32 * g, kTileGroups, pk + 2 * g, local);
                         uint32_t any = 0;
                         for (int i = 0; i < kTileGroups; i++) any |= local[i];
                         tile_dirty[g / kTileGroups] = any ? 1 : 0;
@@ -314,7 +339,8 @@ struct HostPackJob {
 };
 
 HostPackJob *host_pack_start(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
-                             int64_t bases_per_block, int threads, uint8_t *tile_dirty, int64_t blocks_per_chunk) {
+                             int64_t bases_per_block, int threads, uint8_t *tile_dirty, int64_t blocks_per_chunk,
+                             int64_t ring_blocks) {
     const int64_t n_groups = n_bases / 32, gpb = bases_per_block / 32;
     const int64_t blocks = (n_groups + gpb - 1) / gpb;
     const int64_t chunks = blocks_per_chunk > 0 ? (blocks + blocks_per_chunk - 1) / blocks_per_chunk : 0;
@@ -325,7 +351,8 @@ HostPackJob *host_pack_start(const uint8_t *h_ascii, int64_t n_bases, uint32_t *
     hp->job.n_groups = n_groups;
     hp->job.groups_per_block = gpb;
     hp->job.n_blocks = blocks;
-    hp->job.fn = choose_pack(0);
+    hp->job.fn = choose_pack(0, ring_blocks > 0);
+    hp->job.ring_blocks = ring_blocks;
     hp->job.tile_dirty = tile_dirty;
     hp->job.blocks_per_chunk = blocks_per_chunk;
     Pool &pool = Pool::get();
@@ -355,8 +382,20 @@ bool host_pack_claim_raw(HostPackJob *hp, int64_t c) {
     uint8_t expect = 0;
     return hp->job.chunk_state[(size_t)c].compare_exchange_strong(expect, 2, std::memory_order_acq_rel);
 }
-bool host_pack_help(HostPackJob *hp) { return hp->job.run_one(); }
+// the submitting thread lends a hand -- except in ring mode, where it is the one that frees the slots the
+// packers wait for and must not wait itself
+bool host_pack_help(HostPackJob *hp) { return hp->job.ring_blocks > 0 ? false : hp->job.run_one(); }
+// blocks [b0, b1) all packed?
+bool host_pack_blocks_ready(HostPackJob *hp, int64_t b0, int64_t b1) {
+    for (int64_t b = b0; b < b1; b++)
+        if (!hp->job.done[(size_t)b].load(std::memory_order_acquire)) return false;
+    return true;
+}
+// ring mode: every block below `blocks` has been copied away (or will never be packed)
+void host_pack_release(HostPackJob *hp, int64_t blocks) { hp->job.free_upto.store(blocks, std::memory_order_release); }
 void host_pack_finish(HostPackJob *hp) {
+    // an early exit (error path) must not leave workers waiting for ring slots
+    if (hp->job.finished.load(std::memory_order_acquire) < hp->job.n_blocks) hp->job.abort.store(true);
     Pool::get().finish(&hp->job);
     delete hp;
 }
@@ -386,7 +425,7 @@ extern "C" __attribute__((visibility("default"))) int panib_pack_host(const uint
         pack_fence();
         return PANIB_OK;
     }
-    HostPackJob *hp = host_pack_start(h_ascii, n_bases, h_packed, h_mask, 1 << 18, threads, nullptr, 0);
+    HostPackJob *hp = host_pack_start(h_ascii, n_bases, h_packed, h_mask, 1 << 18, threads, nullptr, 0, 0);
     host_pack_finish(hp);
     return PANIB_OK;
 }
@@ -402,7 +441,7 @@ extern "C" __attribute__((visibility("default"))) int panib_pack_host_tiles(cons
         return PANIB_E_ARG;
     }
     if (n_bases == 0) return PANIB_OK;
-    HostPackJob *hp = host_pack_start(h_ascii, n_bases, h_packed, h_mask, 64 * PANIB_TILE_BASES, threads, h_tile_dirty, 0);
+    HostPackJob *hp = host_pack_start(h_ascii, n_bases, h_packed, h_mask, 64 * PANIB_TILE_BASES, threads, h_tile_dirty, 0, 0);
     host_pack_finish(hp);
     return PANIB_OK;
 }

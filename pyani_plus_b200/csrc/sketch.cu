@@ -9,6 +9,7 @@
 // (kmer_hash.cuh), and the only global writes are the ~1/scaled surviving hashes, inserted into
 // value-range buckets of the genome's row so that a per-bucket sort yields the globally sorted,
 // duplicate-free sketch.
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -924,8 +925,11 @@ extern "C" int panib_sketch_ascii_host_hash_only(const uint8_t *h_ascii, uint8_t
 namespace panib {
 struct HostPackJob;
 HostPackJob *host_pack_start(const uint8_t *h_ascii, int64_t n_bases, uint32_t *h_packed, uint32_t *h_mask,
-                             int64_t bases_per_block, int threads, uint8_t *tile_dirty, int64_t blocks_per_chunk);
+                             int64_t bases_per_block, int threads, uint8_t *tile_dirty, int64_t blocks_per_chunk,
+                             int64_t ring_blocks);
 bool host_pack_chunk_ready(HostPackJob *hp, int64_t c);
+bool host_pack_blocks_ready(HostPackJob *hp, int64_t b0, int64_t b1);
+void host_pack_release(HostPackJob *hp, int64_t blocks);
 bool host_pack_claim_raw(HostPackJob *hp, int64_t c);
 bool host_pack_help(HostPackJob *hp);
 void host_pack_finish(HostPackJob *hp);
@@ -934,6 +938,7 @@ void host_pack_finish(HostPackJob *hp);
 constexpr int kIngestMaxChunks = 64;
 constexpr int64_t kIngestBlockTiles = 64;  // packing block: 64 tiles = 256 Ki bases
 constexpr int kIngestMaskSlots = 3, kIngestRawSlots = 3;
+constexpr int kIngestRingEvents = 64;  // copies of ring groups in flight
 constexpr int kMaskWords = kTileBases / 32;  // mask words per tile
 
 static int64_t ingest_chunk_tiles(int64_t total_tiles) {
@@ -950,11 +955,11 @@ extern "C" int64_t panib_ingest_scratch_bytes(int64_t n_bases) {
 }
 
 // what the last panib_sketch_packed_host call of this thread moved: {bytes host->device, chunks, chunks sent as
-// ASCII, dirty tiles}
-static thread_local int64_t g_ingest_last[4] = {0, 0, 0, 0};
-extern "C" int panib_ingest_last(int64_t *out4) {
-    if (!out4) return PANIB_E_ARG;
-    for (int i = 0; i < 4; i++) out4[i] = g_ingest_last[i];
+// ASCII, dirty tiles, bytes of the packed-word ring (0 = whole-stream buffer), 1 if the call was a measuring one}
+static thread_local int64_t g_ingest_last[6] = {0, 0, 0, 0, 0, 0};
+extern "C" int panib_ingest_last(int64_t *out6) {
+    if (!out6) return PANIB_E_ARG;
+    for (int i = 0; i < 6; i++) out6[i] = g_ingest_last[i];
     return PANIB_OK;
 }
 
@@ -992,6 +997,7 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     struct Res {
         cudaStream_t copy_stream = nullptr;
         cudaEvent_t copied[kIngestMaxChunks], ready = nullptr, mask_free[kIngestMaskSlots], raw_free[kIngestRawSlots];
+        cudaEvent_t ring_ev[kIngestRingEvents];
         int device = -1;
         std::vector<uint8_t> dirty;
         std::vector<uint32_t> ids;
@@ -1001,6 +1007,7 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     PANIB_CUDA(cudaGetDevice(&dev));
     if (!R.copy_stream || R.device != dev) {
         PANIB_CUDA(cudaStreamCreateWithFlags(&R.copy_stream, cudaStreamNonBlocking));
+        for (auto &e : R.ring_ev) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : R.copied) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : R.mask_free) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : R.raw_free) PANIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1033,11 +1040,51 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     }
     uint8_t *d_mask_stage = d_scratch, *d_raw = d_scratch ? d_scratch + kIngestMaskSlots * mask_slot : nullptr;
 
+    // Packed output as a small RING inside h_packed (16 MB) instead of the whole-stream buffer: a slot is re-written
+    // while it is still in the last-level cache and the DMA engine reads it from there, so packing costs the
+    // host's DRAM one read of the ASCII and nothing else (the whole-stream buffer with its streaming stores costs a
+    // write and a read of the packed form on top: 1.5 instead of 1.0 byte of DRAM traffic per base, on hosts whose
+    // memory system is what bounds the pipeline).  Whether the DMA engine reads cache-resident lines fast depends
+    // on where the host put the process relative to the GPU's root port: measured 39.1 -> 32.3 ms per 5 Gbp on one
+    // 16-core box and 40.4 -> 48 ms on another.  So the library MEASURES: per thread and stream size the first
+    // call warms up, the second times the whole-stream form, the third the ring, and the faster one is kept
+    // (the sketches do not depend on it).  PANIB_INGEST_RING_MB pins it: 0 = never, N = always, N MB.
+    const int64_t block_words = kIngestBlockTiles * (kTileBases / 16);
+    const int64_t total_blocks = (total_tiles + kIngestBlockTiles - 1) / kIngestBlockTiles;
+    struct Tune {
+        int64_t key = -1;
+        int calls = 0;
+        double seconds[2] = {0.0, 0.0};  // [0] whole-stream form, [1] ring
+    };
+    static thread_local Tune tune;
+    int64_t ring_blocks = 0, group_blocks = 1;
+    int tune_slot = -1;  // >= 0: this call is a measurement of that form
+    if (h_ascii) {
+        const char *e = getenv("PANIB_INGEST_RING_MB");
+        int64_t mb = e ? atoll(e) : 16;
+        if (!e) {  // no wish: measure, then keep the faster form (streams below 32 rings: not worth measuring)
+            if (total_blocks * block_words * 4 < 32 * (mb << 20)) mb = 0;
+            else {
+                if (tune.key != total_blocks) tune = Tune{total_blocks, 0, {0.0, 0.0}};
+                const int call = tune.calls++;
+                if (call == 0) mb = 0;
+                else if (call == 1) { mb = 0; tune_slot = 0; }
+                else if (call == 2) tune_slot = 1;
+                else if (!(tune.seconds[1] < 0.97 * tune.seconds[0])) mb = 0;
+            }
+        }
+        ring_blocks = (mb << 20) / (block_words * 4);
+        group_blocks = ring_blocks / 4 < 16 ? ring_blocks / 4 : 16;
+        if (group_blocks < 1) group_blocks = 1;
+        ring_blocks = ring_blocks / group_blocks * group_blocks;
+        if (ring_blocks < 2 * group_blocks || ring_blocks >= total_blocks) ring_blocks = 0;  // not worth it / fits anyway
+    }
+    const auto tune_t0 = std::chrono::steady_clock::now();
     HostPackJob *job = nullptr;
     if (h_ascii) {
         if (sparse) R.dirty.assign((size_t)total_tiles, 0);
         job = host_pack_start(h_ascii, n_bases, h_packed, h_mask, kIngestBlockTiles * kTileBases, host_threads,
-                              sparse ? R.dirty.data() : nullptr, per / kIngestBlockTiles);
+                              sparse ? R.dirty.data() : nullptr, per / kIngestBlockTiles, ring_blocks);
     }
     auto fail = [&](int code) {
         if (job) host_pack_finish(job);
@@ -1072,11 +1119,13 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
         return launch_hash_range(d_packed, d_mask, d_tile_off, n_genomes, from, upto, k, seed, max_hash, d_nb, d_bmul,
                                  d_table, row_stride, d_flags, d_status, st);
     };
-    auto send_packed = [&](int c) -> int {
+    auto send_packed = [&](int c, bool words_sent = false) -> int {
         const int64_t t0 = c * per, t1 = (c + 1) * per < total_tiles ? (c + 1) * per : total_tiles, n = t1 - t0;
-        PANIB_CUDA_JOB(cudaMemcpyAsync(d_packed + t0 * (kTileBases / 16), h_packed + t0 * (kTileBases / 16),
-                                       (size_t)n * (kTileBases / 4), cudaMemcpyHostToDevice, cs));
-        moved[0] += n * (kTileBases / 4);
+        if (!words_sent) {  // (ring mode has sent them group by group)
+            PANIB_CUDA_JOB(cudaMemcpyAsync(d_packed + t0 * (kTileBases / 16), h_packed + t0 * (kTileBases / 16),
+                                           (size_t)n * (kTileBases / 4), cudaMemcpyHostToDevice, cs));
+            moved[0] += n * (kTileBases / 4);
+        }
         uint32_t *hm = h_mask + t0 * kMaskWords, *dm = d_mask + t0 * kMaskWords;
         int nd = 0, slot = -1;
         bool scatter = false;
@@ -1146,6 +1195,114 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     };
 
     int head = 0, tail = n_chunks;  // chunks [head, tail) have not been sent yet
+    if (job && ring_blocks > 0) {
+        // ---- ring mode: packed words leave group by group as soon as their blocks are packed; a group's ring slots
+        // are handed back to the pool when its copy has completed
+        const int64_t bpc = per / kIngestBlockTiles;
+        struct Pending { int ev; int64_t end_block; } pend[kIngestRingEvents];
+        int pend_at = 0, pend_n = 0, ev_next = 0;
+        int64_t sent_block = 0;
+        auto drain = [&](bool wait_oldest) {  // completed copies -> free ring slots
+            bool any = false;
+            while (pend_n > 0) {
+                cudaError_t q = cudaEventQuery(R.ring_ev[pend[pend_at].ev]);
+                if (q == cudaErrorNotReady) {
+                    if (!wait_oldest) break;
+                    q = cudaEventSynchronize(R.ring_ev[pend[pend_at].ev]);
+                }
+                if (q != cudaSuccess) break;
+                wait_oldest = false;
+                if (pend[pend_at].end_block >= 0) host_pack_release(job, pend[pend_at].end_block);
+                pend_at = (pend_at + 1) % kIngestRingEvents;
+                pend_n--;
+                any = true;
+            }
+            cudaGetLastError();  // cudaErrorNotReady is not an error
+            return any;
+        };
+        constexpr int64_t kRawPiece = 4 << 20;
+        int raw_c = -1, raw_slot_at = 0;
+        int64_t raw_off = 0;
+        auto raw_piece = [&]() -> int {  // next piece of raw chunk raw_c; the last one hands the chunk to K0 + K1
+            const int64_t t0 = raw_c * per, t1 = (raw_c + 1) * per < total_tiles ? (raw_c + 1) * per : total_tiles;
+            const int64_t bytes = (t1 - t0) * kTileBases;
+            uint8_t *dst = d_raw + raw_slot_at * raw_slot;
+            const int64_t piece = bytes - raw_off < kRawPiece ? bytes - raw_off : kRawPiece;
+            if (pend_n == kIngestRingEvents) drain(true);
+            PANIB_CUDA_JOB(cudaMemcpyAsync(dst + raw_off, h_ascii + t0 * kTileBases + raw_off, (size_t)piece,
+                                           cudaMemcpyHostToDevice, cs));
+            moved[0] += piece;
+            raw_off += piece;
+            PANIB_CUDA_JOB(cudaEventRecord(R.ring_ev[ev_next], cs));  // keeps pend_n honest about the link; frees nothing
+            pend[(pend_at + pend_n) % kIngestRingEvents] = Pending{ev_next, -1};
+            pend_n++;
+            ev_next = (ev_next + 1) % kIngestRingEvents;
+            if (raw_off < bytes) return PANIB_OK;
+            PANIB_CUDA_JOB(cudaEventRecord(R.copied[raw_c], cs));
+            PANIB_CUDA_JOB(cudaStreamWaitEvent(st, R.copied[raw_c], 0));
+            int rc2 = panib_pack_ascii(dst, bytes, d_packed + t0 * (kTileBases / 16), d_mask + t0 * kMaskWords, stream);
+            if (rc2) return fail(rc2);
+            PANIB_CUDA_JOB(cudaEventRecord(R.raw_free[raw_slot_at], st));
+            rc2 = hash_chunk(raw_c);
+            raw_c = -1;
+            return rc2 ? fail(rc2) : PANIB_OK;
+        };
+        while (head < tail) {
+            bool progress = drain(false);
+            const int64_t cb1 = (head + 1) * bpc < total_blocks ? (head + 1) * bpc : total_blocks;
+            while (sent_block < cb1) {
+                int64_t g1 = (sent_block / group_blocks + 1) * group_blocks;  // groups never wrap around the ring
+                if (g1 > cb1) g1 = cb1;
+                if (!host_pack_blocks_ready(job, sent_block, g1)) break;
+                if (pend_n == kIngestRingEvents) drain(true);
+                const int64_t w0 = sent_block * block_words;
+                int64_t w1 = g1 * block_words;
+                if (w1 > total_tiles * (kTileBases / 16)) w1 = total_tiles * (kTileBases / 16);
+                PANIB_CUDA_JOB(cudaMemcpyAsync(d_packed + w0, h_packed + (sent_block % ring_blocks) * block_words,
+                                               (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, cs));
+                moved[0] += (w1 - w0) * 4;
+                PANIB_CUDA_JOB(cudaEventRecord(R.ring_ev[ev_next], cs));
+                pend[(pend_at + pend_n) % kIngestRingEvents] = Pending{ev_next, g1};
+                pend_n++;
+                ev_next = (ev_next + 1) % kIngestRingEvents;
+                sent_block = g1;
+                progress = true;
+            }
+            if (sent_block >= cb1) {  // every word of chunk `head` is on its way: mask, then K1
+                rc = send_packed(head++, true);
+                if (rc) return rc;
+                continue;
+            }
+            if (raw_slots > 0 && (pend_n == 0 || raw_eager)) {
+                // The link is idle: give it a PIECE of a raw chunk (4 MB of ASCII, on the same stream, so that it
+                // never competes with a group of the ring for longer than that; whole raw chunks on a stream of
+                // their own halved the ring's share of the link and stalled the packers).
+                if (raw_c < 0) {
+                    if (tail - 1 > head && host_pack_claim_raw(job, tail - 1)) {
+                        raw_c = --tail;
+                        raw_off = 0;
+                        raw_slot_at = raw_used % raw_slots;
+                        if (raw_used >= raw_slots) PANIB_CUDA_JOB(cudaStreamWaitEvent(cs, R.raw_free[raw_slot_at], 0));
+                        raw_used++;
+                        moved[2] += 1;
+                    } else {
+                        raw_slots = 0;  // the pool has reached the tail: everything left is being packed
+                    }
+                }
+                if (raw_c >= 0) {
+                    rc = raw_piece();
+                    if (rc) return rc;
+                    progress = true;
+                }
+            }
+            if (!progress) std::this_thread::yield();
+        }
+        while (raw_c >= 0) {  // the rest of a raw chunk that was under way when the packed chunks ran out
+            rc = raw_piece();
+            if (rc) return rc;
+        }
+        host_pack_release(job, total_blocks + ring_blocks);
+    }
     while (head < tail) {
         if (!job || host_pack_chunk_ready(job, head)) {
             rc = send_packed(head++);
@@ -1169,9 +1326,16 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
         }
         if (!host_pack_help(job)) std::this_thread::yield();
     }
+    if (tune_slot >= 0) {  // a measuring call: until the last byte is on the device
+        PANIB_CUDA_JOB(cudaEventRecord(R.ready, cs));
+        PANIB_CUDA_JOB(cudaEventSynchronize(R.ready));
+        tune.seconds[tune_slot] = std::chrono::duration<double>(std::chrono::steady_clock::now() - tune_t0).count();
+    }
 #undef PANIB_CUDA_JOB
     if (job) host_pack_finish(job);
     for (int i = 0; i < 4; i++) g_ingest_last[i] = moved[i];
+    g_ingest_last[4] = ring_blocks * block_words * 4;
+    g_ingest_last[5] = tune_slot >= 0 ? 1 : 0;
     if (!d_counts) return PANIB_OK;
     return panib_sketch_finalize(d_table, row_stride, n_genomes, d_nb, d_counts, d_flags, d_status, stream);
 }

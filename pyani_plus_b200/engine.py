@@ -416,10 +416,10 @@ class Engine:
 
     def ingest_last(self) -> dict:
         """What the last ``sketch_host`` call of this thread moved over PCIe (``panib_ingest_last``)."""
-        out = (ctypes.c_int64 * 4)()
+        out = (ctypes.c_int64 * 6)()
         _check(self.lib.panib_ingest_last(out))
         return {"h2d_bytes": int(out[0]), "chunks": int(out[1]), "chunks_as_ascii": int(out[2]),
-                "dirty_tiles": int(out[3])}
+                "dirty_tiles": int(out[3]), "ring_bytes": int(out[4]), "measuring_call": bool(out[5])}
 
     def hash_packed(self, plan: "StreamPlan", bufs: dict, tab: dict, k: int, *, seed: int = 42) -> None:
         """K1 hashing only: rows are left as bucketed hash sets (finalize separately)."""

@@ -551,8 +551,15 @@ def test_ingest_pipeline_paths_agree(eng, monkeypatch: pytest.MonkeyPatch) -> No
     run(h_pinned, PANIB_INGEST_RAW="2")              # raw chunks from the tail as long as any is free
     run(h_pinned, PANIB_INGEST_RAW="0")              # sparse mask only
     run(h_pinned, PANIB_INGEST_SPARSE="0")           # dense mask, in order
+    # packed words through a small ring inside h_packed (1 MB = 16 blocks here, so that it wraps several times)
+    run(h_pageable, PANIB_INGEST_RING_MB="1")
+    run(h_pinned, PANIB_INGEST_RING_MB="1")
+    run(h_pinned, PANIB_INGEST_RING_MB="1", PANIB_INGEST_RAW="2")
+    run(h_pinned, PANIB_INGEST_RING_MB="1", PANIB_INGEST_SPARSE="0")
+    run(h_pinned, PANIB_INGEST_RING_MB="0")          # the whole-stream buffer with streaming stores
     scratch = bufs.pop("ingest_scratch")             # no device scratch at all: dense mask, in order
     run(h_pinned)
+    run(h_pinned, PANIB_INGEST_RING_MB="1")
     bufs["ingest_scratch"] = scratch[: scratch.numel() // 8]  # room for the mask ring only
     run(h_pinned, PANIB_INGEST_RAW="2")
 

@@ -1,0 +1,21 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "ingest or pipeline" > $OUT/r2s_tests.log 2>&1; echo "rc=$?" >> $OUT/r2s_tests.log
+tail -4 $OUT/r2s_tests.log
+B="python bench.py --workload config3 --steps 6 --warmup 3 --no-cpu-baseline"
+for mb in 16 32 24; do
+  PANIB_INGEST_RING_MB=$mb timeout 600 $B > $OUT/r2s_bench_ring$mb.json 2> $OUT/r2s_bench_ring$mb.err
+done
+PANIB_INGEST_RING_MB=16 PANIB_INGEST_RAW=0 timeout 600 $B > $OUT/r2s_bench_ring16noraw.json 2> $OUT/r2s_bench_ring16noraw.err
+PANIB_INGEST_RING_MB=32 PANIB_INGEST_RAW=0 timeout 600 $B > $OUT/r2s_bench_ring32noraw.json 2> $OUT/r2s_bench_ring32noraw.err
+python - <<'PY'
+import json
+for v in ("ring16", "ring24", "ring32", "ring16noraw", "ring32noraw"):
+    try:
+        d = json.loads(open(f"gpurun_out/r2s_bench_{v}.json").read().strip().splitlines()[-1])
+        e = d["e2e"]
+        print(v, "value ms", round(d["ms_per_step"], 2), "e2e ms", round(e["ms_per_step"], 2), {k: e["ingest"][k] for k in ("h2d_bytes", "chunks_as_ascii", "dirty_tiles")}, "parity", d["parity"]["ok"])
+    except Exception as exc:
+        print(v, "failed", exc)
+PY
