@@ -1059,7 +1059,10 @@ extern "C" int panib_sketch_packed_host(const uint8_t *h_ascii, uint32_t *h_pack
     static thread_local Tune tune;
     int64_t ring_blocks = 0, group_blocks = 1;
     int tune_slot = -1;  // >= 0: this call is a measurement of that form
-    if (h_ascii) {
+    // in ring mode the submitting thread frees the slots and never packs: it needs at least one pool worker
+    const int pool_threads = panib_host_threads();
+    const bool has_workers = (host_threads > 0 && host_threads < pool_threads ? host_threads : pool_threads) >= 2;
+    if (h_ascii && has_workers) {
         const char *e = getenv("PANIB_INGEST_RING_MB");
         int64_t mb = e ? atoll(e) : 16;
         if (!e) {  // no wish: measure, then keep the faster form (streams below 32 rings: not worth measuring)

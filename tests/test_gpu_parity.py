@@ -530,13 +530,13 @@ def test_ingest_pipeline_paths_agree(eng, monkeypatch: pytest.MonkeyPatch) -> No
     want_packed, want_mask = bufs["packed"].clone(), bufs["mask"].clone()
     want = [oracle.sketch_records(recs, k, scaled) for recs in genomes]
 
-    def run(h_ascii, **env: str) -> None:
+    def run(h_ascii, threads: int = 0, **env: str) -> None:
         for key, val in env.items():
             monkeypatch.setenv(key, val)
         bufs["packed"].fill_(-1)
         bufs["mask"].fill_(0x55555555)
         tab["table"].fill_(7)
-        eng.sketch_host(h_ascii, plan, bufs, tab, k)
+        eng.sketch_host(h_ascii, plan, bufs, tab, k, threads=threads)
         assert eng.check_status() == 0
         for key in env:
             monkeypatch.delenv(key)
@@ -557,6 +557,8 @@ def test_ingest_pipeline_paths_agree(eng, monkeypatch: pytest.MonkeyPatch) -> No
     run(h_pinned, PANIB_INGEST_RING_MB="1", PANIB_INGEST_RAW="2")
     run(h_pinned, PANIB_INGEST_RING_MB="1", PANIB_INGEST_SPARSE="0")
     run(h_pinned, PANIB_INGEST_RING_MB="0")          # the whole-stream buffer with streaming stores
+    run(h_pinned, 1, PANIB_INGEST_RING_MB="1")       # one host thread: it packs itself, so no ring (it would wait for itself)
+    run(h_pinned, 2, PANIB_INGEST_RING_MB="1")       # the submitting thread and one worker
     scratch = bufs.pop("ingest_scratch")             # no device scratch at all: dense mask, in order
     run(h_pinned)
     run(h_pinned, PANIB_INGEST_RING_MB="1")
