@@ -53,22 +53,42 @@ WORKLOADS = {
 }
 
 
-def kernel_source_sha() -> str:
-    """sha256 over the CUDA sources the library is built from: ties an ncu capture to the kernels it measured."""
+# translation unit + headers each captured kernel is compiled from (include graph of csrc/): an ncu capture
+# stays evidence for as long as THESE files are unchanged, whatever happens to the other kernels' sources
+KERNEL_SOURCES = {
+    "k1": ("sketch.cu", "kmer_hash.cuh", "pack.cuh", "common.cuh"),
+    "k2_index": ("index.cu", "common.cuh"),
+    "k2_probe": ("pairwise.cu", "common.cuh"),
+}
+
+
+def kernel_source_sha(kernel: str | None = None) -> str:
+    """sha256 over the CUDA sources a kernel is built from (``kernel`` in KERNEL_SOURCES: its translation unit,
+    the headers it includes and the preprocessor lines of include/panib200.h -- the only part of the C header
+    that reaches device code; None = every CUDA source of the library and the whole header): ties an ncu
+    capture to the code it measured."""
     import hashlib
 
     h = hashlib.sha256()
     csrc = ROOT / "pyani_plus_b200" / "csrc"
-    for f in sorted(list(csrc.glob("*.cu")) + list(csrc.glob("*.cuh")) + [ROOT / "include" / "panib200.h"]):
-        h.update(f.name.encode())
-        h.update(f.read_bytes())
+    header = ROOT / "include" / "panib200.h"
+    if kernel is None:
+        for f in sorted([*csrc.glob("*.cu"), *csrc.glob("*.cuh"), header]):
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    else:
+        for name in sorted(KERNEL_SOURCES[kernel]):
+            h.update(name.encode())
+            h.update((csrc / name).read_bytes())
+        h.update(b"".join(ln for ln in header.read_bytes().splitlines(keepends=True) if ln.lstrip().startswith(b"#")))
     return h.hexdigest()[:16]
 
 
 def ncu_capture(workload: str, kernel: str) -> dict | None:
     """Per-launch ncu numbers of ``kernel`` ("k1", "k2_probe", "k2_index") at ``workload`` from the newest
     profiles/ncu_r*.json (written by tools/ncu_to_json.py from an ``ncu --set full`` capture) -- but only if
-    that capture was taken from the kernel sources this tree holds; otherwise None (stale = not evidence)."""
+    that capture was taken from the sources this tree builds the kernel from; otherwise None (stale = not
+    evidence)."""
     files = sorted((ROOT / "profiles").glob("ncu_r*.json"))
     if not files:
         return None
@@ -76,12 +96,14 @@ def ncu_capture(workload: str, kernel: str) -> dict | None:
         data = json.loads(files[-1].read_text())
     except ValueError:
         return None
-    if data.get("source_sha") != kernel_source_sha():
-        return None
     cap = data.get("captures", {}).get(workload, {}).get(kernel)
-    if cap is not None:
-        cap = dict(cap, file=f"profiles/{files[-1].name}")
-    return cap
+    if cap is None:
+        return None
+    if "source_sha" in cap:
+        fresh = cap["source_sha"] == kernel_source_sha(kernel)
+    else:  # older files: one hash over the whole library
+        fresh = data.get("source_sha") == kernel_source_sha()
+    return dict(cap, file=f"profiles/{files[-1].name}") if fresh else None
 
 
 def config_dict(workload: str, n_gpus: int) -> dict:

@@ -91,10 +91,17 @@ PANIB_API int panib_plan_buckets(int64_t n_kmers, uint64_t scaled, double slack,
 /* ---- ingest (host): FASTA text -> base-stream form ------------------------------------------ */
 /* Parses decompressed FASTA text exactly as pyani_plus/utils.py:40-90 (fasta_bytes_iterator) does and
  * writes the records' sequences back to back with one 'N' between records.  dst may be NULL to only
- * measure.  Returns the stream-form length, or PANIB_E_ARG.  out4 = n_records, total_bases,
+ * measure; n bytes are always enough for dst.  Returns the stream-form length, or PANIB_E_ARG.  out4 = n_records, total_bases,
  * offset and length (in text) of the first record's title. */
 PANIB_API int64_t panib_fasta_to_stream(const uint8_t *text, int64_t n, uint8_t *dst, int64_t dst_cap,
                                         int64_t *out4);
+
+/* ---- results (host): decimal text of a sketch ---------------------------------------------- */
+/* Writes n unsigned 64-bit integers in decimal, `sep` between them (sep == 0: back to back): the "mins" array
+ * of a sourmash signature file and the input of its "md5sum" (what `sourmash scripts singlesketch` writes for
+ * pyani_plus/methods/sourmash.py:57-83).  Returns the bytes written, or PANIB_E_ARG if dst_cap is too small
+ * (21 * n always suffices). */
+PANIB_API int64_t panib_format_u64(const uint64_t *values, int64_t n, int sep, char *dst, int64_t dst_cap);
 
 /* ---- stage 0: ASCII base stream -> packed 2-bit + validity mask --------------------------- */
 /* n_bases must be a multiple of 32.  Upper-cases; any byte other than A,C,G,T is invalid. */

@@ -78,75 +78,4 @@ extern "C" int panib_plan_buckets(int64_t n_kmers, uint64_t scaled, double slack
     return PANIB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// FASTA text -> base-stream form, on the host.  Restates pyani_plus/utils.py:40-90
-// (fasta_bytes_iterator): a record starts at a line whose FIRST byte is '>', lines are split at '\n'
-// only, anything before the first record is skipped, and the sequence is every byte of the following
-// lines with space, tab, CR and LF removed.  Records are written back to back with ONE 'N' between
-// them (the invalid separator of the base stream).  This replaces the per-line Python loop for the
-// drop-in path (at scale, ingest dominates the GPU time by orders of magnitude).
-// ------------------------------------------------------------------------------------------------
-namespace {
-struct FastaScan {
-    int64_t n_records = 0, total_bases = 0, title_off = -1, title_len = 0, written = 0;
-};
-
-FastaScan fasta_walk(const uint8_t *text, int64_t n, uint8_t *dst, int64_t cap, bool *overflow) {
-    FastaScan r;
-    int64_t pos = 0;
-    bool in_record = false;
-    while (pos < n) {
-        const uint8_t *nl = (const uint8_t *)memchr(text + pos, '\n', (size_t)(n - pos));
-        const int64_t end = nl ? (int64_t)(nl - text) : n;  // line = [pos, end), newline excluded
-        if (end > pos && text[pos] == '>') {
-            if (r.n_records == 0) {  // title of the first record, right-stripped
-                int64_t te = end;
-                while (te > pos + 1 && (text[te - 1] == ' ' || text[te - 1] == '\t' || text[te - 1] == '\r' ||
-                                        text[te - 1] == '\n' || text[te - 1] == '\v' || text[te - 1] == '\f'))
-                    te--;
-                r.title_off = pos + 1;
-                r.title_len = te - (pos + 1);
-            }
-            if (r.n_records > 0) {  // separator between records
-                if (dst) { if (r.written < cap) dst[r.written] = 'N'; else *overflow = true; }
-                r.written++;
-            }
-            r.n_records++;
-            in_record = true;
-        } else if (in_record) {
-            for (int64_t i = pos; i < end; i++) {
-                const uint8_t c = text[i];
-                if (c == ' ' || c == '\t' || c == '\r') continue;
-                if (dst) { if (r.written < cap) dst[r.written] = c; else *overflow = true; }
-                r.written++;
-                r.total_bases++;
-            }
-        }
-        pos = end + 1;
-    }
-    return r;
-}
-}  // namespace
-
-// Pass 1 (dst == NULL) or pass 2: returns the stream-form length (bases + separators), or
-// PANIB_E_ARG if dst is too small.  out[0..3] = n_records, total_bases, title_off, title_len.
-extern "C" int64_t panib_fasta_to_stream(const uint8_t *text, int64_t n, uint8_t *dst, int64_t dst_cap,
-                                         int64_t *out4) {
-    if (!text || n < 0) {
-        set_error("panib_fasta_to_stream: bad arguments");
-        return PANIB_E_ARG;
-    }
-    bool overflow = false;
-    const FastaScan r = fasta_walk(text, n, dst, dst_cap, &overflow);
-    if (overflow) {
-        set_error("panib_fasta_to_stream: destination too small (%lld needed)", (long long)r.written);
-        return PANIB_E_ARG;
-    }
-    if (out4) {
-        out4[0] = r.n_records;
-        out4[1] = r.total_bases;
-        out4[2] = r.title_off;
-        out4[3] = r.title_len;
-    }
-    return r.written;
-}
+// (panib_fasta_to_stream and panib_format_u64, the host-side text routines, live in hostio.cpp)

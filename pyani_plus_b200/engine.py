@@ -118,6 +118,8 @@ def load_library() -> ctypes.CDLL:
     L.panib_ani_host.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]
     L.panib_fasta_to_stream.restype = _i64
     L.panib_fasta_to_stream.argtypes = [ctypes.c_char_p, _i64, _vp, _i64, ctypes.POINTER(_i64)]
+    L.panib_format_u64.restype = _i64
+    L.panib_format_u64.argtypes = [_vp, _i64, _i32, _vp, _i64]
     L.panib_synth_ascii.restype = _i32
     L.panib_synth_ascii.argtypes = [_u64, _i64, _i64, _i64, _vp, _vp]
     _lib = L
@@ -157,16 +159,27 @@ def fasta_to_stream(text: bytes) -> tuple[np.ndarray, int, int, bytes | None]:
     """
     lib = load_library()
     out4 = (_i64 * 4)()
-    need = int(lib.panib_fasta_to_stream(text, len(text), None, 0, out4))
-    if need < 0:
-        _check(need)
-    stream = np.empty(need, dtype=np.uint8)
-    if need:
-        got = int(lib.panib_fasta_to_stream(text, len(text), stream.ctypes.data, need, out4))
-        if got != need:
-            _check(got if got < 0 else -2)
+    # one pass: the stream form is never longer than the text (every record gives up its title line and gets at
+    # most one separator), so the text's size is a safe destination and the result is a view of its front
+    buf = np.empty(max(len(text), 1), dtype=np.uint8)
+    got = int(lib.panib_fasta_to_stream(text, len(text), buf.ctypes.data, buf.size, out4))
+    if got < 0:
+        _check(got)
     title = text[out4[2]: out4[2] + out4[3]] if out4[2] >= 0 else None
-    return stream, int(out4[0]), int(out4[1]), title
+    return buf[:got], int(out4[0]), int(out4[1]), title
+
+
+def format_u64(values: np.ndarray, sep: bytes = b",") -> bytes:
+    """Decimal text of uint64 values, ``sep`` (one byte, or b"" for none) between them (``panib_format_u64``)."""
+    v = np.ascontiguousarray(values, dtype=np.uint64)
+    if len(sep) > 1:
+        msg = "sep must be one byte or empty"
+        raise ValueError(msg)
+    out = ctypes.create_string_buffer(21 * v.size + 1)
+    got = int(load_library().panib_format_u64(v.ctypes.data, v.size, sep[0] if sep else 0, out, 21 * v.size + 1))
+    if got < 0:
+        _check(got)
+    return ctypes.string_at(out, got)
 
 
 def pack_host(ascii_stream: np.ndarray, threads: int = 0) -> tuple[np.ndarray, np.ndarray]:

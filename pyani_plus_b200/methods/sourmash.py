@@ -95,7 +95,8 @@ def sketch_entries(  # noqa: PLR0913
 
     gunzip + FASTA parsing (C, GIL released) run on a thread pool a bounded window ahead; genomes are
     sketched in batches of ``PREPARE_BATCH_BYTES``; every sketch is written as sourmash ``.sig`` JSON plus
-    the binary side-cache, and remembered for this process.
+    the binary side-cache (by the same pool: decimal formatting in C, md5 and file writes release the GIL),
+    and remembered for this process.
     """
     from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
 
@@ -105,20 +106,27 @@ def sketch_entries(  # noqa: PLR0913
     pending: list[tuple[str, Path, np.ndarray]] = []
     pending_bytes = 0
 
+    def write_one(md5: str, fasta_filename: Path, hashes: np.ndarray) -> tuple[Path, dict]:
+        # formatting, md5 and file writes release the GIL: the batch's signatures are written by the pool
+        sig_path = cache / f"{md5}.sig"
+        sigfile.write_sig(sig_path, filename=str(fasta_filename), name=md5, ksize=ksize, max_hash=max_hash,
+                          hashes=hashes)
+        sig = {"name": md5, "filename": str(fasta_filename), "ksize": ksize, "seed": 42,
+               "max_hash": max_hash, "md5sum": "", "hashes": hashes}
+        sigfile.write_side_cache(sig_path, sig)
+        return sig_path, sig
+
     def flush() -> Iterator[tuple[str, np.ndarray]]:
         nonlocal pending_bytes
         if pending:
             table = get_engine().sketch_genomes([recs for _, _, recs in pending], ksize, scaled)
-            for (md5, fasta_filename, _), hashes in zip(pending, table.to_host(), strict=True):
-                sig_path = cache / f"{md5}.sig"
-                sigfile.write_sig(sig_path, filename=str(fasta_filename), name=md5, ksize=ksize,
-                                  max_hash=max_hash, hashes=hashes)
-                sig = {"name": md5, "filename": str(fasta_filename), "ksize": ksize, "seed": 42,
-                       "max_hash": max_hash, "md5sum": "", "hashes": hashes}
-                sigfile.write_side_cache(sig_path, sig)
+            writes = [pool.submit(write_one, md5, fasta_filename, hashes)
+                      for (md5, fasta_filename, _), hashes in zip(pending, table.to_host(), strict=True)]
+            for (md5, _, _), done in zip(pending, writes, strict=True):
+                sig_path, sig = done.result()
                 if len(_sig_memo) < SIG_MEMO_MAX:
                     _sig_memo[sig_path] = (sig_path.stat().st_mtime_ns, sig)
-                yield md5, hashes
+                yield md5, sig["hashes"]
             pending.clear()
             pending_bytes = 0
 
@@ -136,7 +144,7 @@ def sketch_entries(  # noqa: PLR0913
             pending_bytes += int(stream_bytes.size)
             if pending_bytes >= PREPARE_BATCH_BYTES:
                 yield from flush()
-    yield from flush()
+        yield from flush()
 
 
 def sketches_for(  # noqa: PLR0913

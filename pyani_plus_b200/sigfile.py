@@ -28,15 +28,22 @@ _SIDE_MAGIC = b"PANIBSK1"
 _SIDE_HEADER = struct.Struct("<8sIIQQQQ")  # magic, ksize, seed, max_hash, count, sig_size, sig_mtime_ns
 
 
+def _mins_text(hashes: np.ndarray) -> bytes:
+    """The hashes in decimal, comma-separated (C formatter of the library: ``panib_format_u64``)."""
+    from pyani_plus_b200 import engine  # noqa: PLC0415
+
+    return engine.format_u64(hashes, b",")
+
+
 def sketch_md5sum(hashes: np.ndarray, ksize: int) -> str:
     """sourmash's sketch checksum: md5 of ``str(ksize)`` followed by every hash in decimal."""
-    return hashlib.md5((str(ksize) + "".join(map(str, hashes.tolist()))).encode()).hexdigest()  # noqa: S324
+    return hashlib.md5(str(ksize).encode() + _mins_text(hashes).replace(b",", b"")).hexdigest()  # noqa: S324
 
 
 def write_sig(path: Path, *, filename: str, name: str, ksize: int, max_hash: int, hashes: np.ndarray) -> None:
     """Write one single-sketch DNA signature file (same keys and key order as sourmash 4.8 / branchwater)."""
-    mins = list(map(str, hashes.astype(np.uint64).tolist()))
-    md5sum = hashlib.md5((str(ksize) + "".join(mins)).encode()).hexdigest()  # noqa: S324
+    mins = _mins_text(hashes)
+    md5sum = hashlib.md5(str(ksize).encode() + mins.replace(b",", b"")).hexdigest()  # noqa: S324
     head = {
         "class": "sourmash_signature",
         "email": "",
@@ -47,13 +54,13 @@ def write_sig(path: Path, *, filename: str, name: str, ksize: int, max_hash: int
     }
     sketch_head = {"num": 0, "ksize": ksize, "seed": SEED, "max_hash": max_hash}
     text = (
-        "[{" + json.dumps(head, separators=(",", ":"))[1:-1]
-        + ',"signatures":[{' + json.dumps(sketch_head, separators=(",", ":"))[1:-1]
-        + ',"mins":[' + ",".join(mins) + "]"
-        + ',"md5sum":"' + md5sum + '","molecule":"DNA"}],"version":0.4}]'
+        b"[{" + json.dumps(head, separators=(",", ":"))[1:-1].encode()
+        + b',"signatures":[{' + json.dumps(sketch_head, separators=(",", ":"))[1:-1].encode()
+        + b',"mins":[' + mins + b"]"
+        + b',"md5sum":"' + md5sum.encode() + b'","molecule":"DNA"}],"version":0.4}]'
     )
     tmp = path.with_suffix(path.suffix + ".tmp")
-    tmp.write_text(text)
+    tmp.write_bytes(text)
     tmp.replace(path)  # never leave a half-written signature in the cache
 
 

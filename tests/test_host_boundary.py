@@ -385,6 +385,65 @@ def test_c_fasta_parser_matches_python_iterator(golden: Path, tmp_path: Path) ->
     assert (stream.size, n, total, title) == (0, 0, 0, None)
 
 
+def test_c_fasta_parser_random_text() -> None:
+    """Seeded random FASTA-like text (long and short lines, blanks / tabs / CRs at every offset of the 16-byte
+    scan, CRLF, stray '>' inside lines, empty records, no final newline): the C parser, in measuring mode and in
+    writing mode, equals the Python iterator of utils.py (the restatement of reference utils.py:40-90)."""
+    import ctypes
+    import io
+    import random
+
+    from pyani_plus_b200 import engine
+
+    lib = engine.load_library()
+    rng = random.Random(20261017)
+    alphabet = [b"A", b"C", b"G", b"T", b"N", b"a", b"c", b"g", b"t", b" ", b"\t", b"\r", b">", b"\x0b", b"-"]
+    weights = [30, 30, 30, 30, 4, 4, 4, 4, 4, 3, 2, 3, 1, 1, 1]
+    for case in range(300):
+        lines = []
+        for _ in range(rng.randrange(0, 12)):
+            kind = rng.random()
+            if kind < 0.25:
+                lines.append(b">" + bytes(rng.choices(b"abc \t\r\x0c", k=rng.randrange(0, 6))))
+            elif kind < 0.35:
+                lines.append(b"")
+            else:
+                lines.append(b"".join(rng.choices(alphabet, weights, k=rng.randrange(1, 70))))
+        eol = b"\r\n" if case % 5 == 0 else b"\n"
+        text = eol.join(lines) + (eol if case % 3 else b"")
+        records = list(utils.fasta_bytes_iterator(io.BytesIO(text)))
+        want = b"N".join(s for _, s in records)
+        stream, n_records, total, title = engine.fasta_to_stream(text)
+        assert stream.tobytes() == want, (case, text)
+        assert (n_records, total) == (len(records), sum(len(s) for _, s in records)), (case, text)
+        assert title == (records[0][0] if records else None), (case, text)
+        out4 = (ctypes.c_int64 * 4)()
+        assert lib.panib_fasta_to_stream(text, len(text), None, 0, out4) == len(want)  # measuring mode
+        if want:  # a destination one byte short is an error, not a truncation
+            small = ctypes.create_string_buffer(len(want) - 1 or 1)
+            assert lib.panib_fasta_to_stream(text, len(text), small, len(want) - 1, out4) == -2
+
+
+def test_format_u64_matches_python_str() -> None:
+    """panib_format_u64 (the decimal text of .sig files) equals str() for every digit count and separator."""
+    import numpy as np
+
+    from pyani_plus_b200 import engine, sigfile
+
+    edge = [0, 1, 9, 10, 11, 99, 100, 101, 999, 1000, 2**32 - 1, 2**32, 2**63, 2**64 - 1, 10**19, 10**19 - 1]
+    edge += [10**d for d in range(20)] + [10**d - 1 for d in range(1, 20)]
+    rng = np.random.default_rng(7)
+    rand = (rng.integers(0, 2**63, 2000, dtype=np.uint64) >> rng.integers(0, 63, 2000).astype(np.uint64)).tolist()
+    values = np.array(edge + rand, dtype=np.uint64)
+    assert engine.format_u64(values, b",") == ",".join(map(str, values.tolist())).encode()
+    assert engine.format_u64(values, b"") == "".join(map(str, values.tolist())).encode()
+    assert engine.format_u64(values[:1], b",") == b"0"
+    assert engine.format_u64(np.array([], dtype=np.uint64)) == b""
+    import hashlib
+
+    assert sigfile.sketch_md5sum(values, 31) == hashlib.md5(("31" + "".join(map(str, values.tolist()))).encode()).hexdigest()  # noqa: S324
+
+
 def test_matrix_cache_skipped_when_too_large_for_sqlite(tmp_path: Path, monkeypatch: pytest.MonkeyPatch) -> None:
     """The reference caches every run matrix as ONE JSON text (db_orm.py:393-466); SQLite takes at most 10^9
     bytes per text, so very large runs skip the cache and the matrix properties rebuild from the comparisons

@@ -5,9 +5,10 @@ roofline fields from (per-launch DRAM traffic, executed warp instructions, pipe 
     python tools/ncu_to_json.py r02 config3 k1=gpurun_out/prof_k1_r02.ncu-rep k2_index=gpurun_out/prof_k2idx_r02.ncu-rep \
         [--sha gpurun_out/source_sha_r02.txt] [--bases 5000000000]
 
-The JSON carries ``source_sha`` = bench.kernel_source_sha() of the CUDA sources the captured library was
-built from (taken from --sha when the capture script recorded it, else computed from the working tree).
-bench.py prints ``traffic: null`` whenever the tree's kernels no longer match that hash.
+Every capture carries ``source_sha`` = bench.kernel_source_sha(<kernel>) of the CUDA sources that kernel was
+built from (taken from --sha when the capture script recorded them on the GPU box -- a JSON object
+{"all": ..., "k1": ..., ...} -- else computed from the working tree).  bench.py prints ``traffic: null``
+whenever the tree's sources of that kernel no longer match the hash.
 """
 from __future__ import annotations
 
@@ -104,7 +105,8 @@ def main() -> None:
     i = 0
     while i < len(args):
         if args[i] == "--sha":
-            sha = Path(args[i + 1]).read_text().strip()
+            txt = Path(args[i + 1]).read_text().strip()
+            sha = json.loads(txt) if txt.startswith("{") else {"all": txt}
             i += 2
         elif args[i] == "--bases":
             bases = int(args[i + 1])
@@ -118,9 +120,11 @@ def main() -> None:
     for key in caps:
         if key == "k1":
             caps[key]["bases"] = bases or n * length
+        if key in bench.KERNEL_SOURCES:
+            caps[key]["source_sha"] = (sha or {}).get(key) or bench.kernel_source_sha(key)
     out_path = ROOT / "profiles" / f"ncu_{tag}.json"
     data = json.loads(out_path.read_text()) if out_path.is_file() else {"captures": {}}
-    data["source_sha"] = sha or bench.kernel_source_sha()
+    data["source_sha"] = (sha or {}).get("all") or bench.kernel_source_sha()
     data["how"] = "ncu --set full --clock-control none, one call of each kernel after warm-up (tools/profile_r2.sh)"
     data["captures"].setdefault(workload, {}).update(caps)
     out_path.write_text(json.dumps(data, indent=1) + "\n")

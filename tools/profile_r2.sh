@@ -10,7 +10,7 @@ TAG=${1:-r02}
 WL=${2:-config3}
 OUT=gpurun_out
 mkdir -p $OUT
-python -c "import bench; print(bench.kernel_source_sha())" > $OUT/source_sha_$TAG.txt
+python -c "import bench, json; print(json.dumps({'all': bench.kernel_source_sha(), **{k: bench.kernel_source_sha(k) for k in bench.KERNEL_SOURCES}}))" > $OUT/source_sha_$TAG.txt
 CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 EAGER="$CMD --no-graph"   # the full captures pick single launches: eager launches keep -s/-c counting simple
 # 1) every launch of the bench command with its device time (cold-cache, serialised: compare shares)
