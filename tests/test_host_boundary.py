@@ -483,3 +483,51 @@ def test_matrix_cache_skipped_when_too_large_for_sqlite(tmp_path: Path, monkeypa
         # the JSON cache keeps 10 significant digits (pandas' to_json, as in the reference); the table is exact
         np.testing.assert_allclose(a.to_numpy(), b.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
         assert list(a.index) == list(b.index) == hashes
+
+
+def test_bulk_insert_literals_and_null_matrices(tmp_path: Path, monkeypatch: pytest.MonkeyPatch) -> None:
+    """insert_comparison_arrays writes the per-call constants as SQL literals (quotes in a uname string are
+    escaped, not executed) and records exactly what the per-row path records; the all-null matrices of the
+    method (aln_length, sim_errors) are cached with the text pandas would produce."""
+    import logging
+    import platform
+    from collections import namedtuple
+
+    import numpy as np
+    import pandas as pd
+
+    from pyani_plus_b200 import db_orm
+
+    logger = logging.getLogger("test")
+    uname = namedtuple("uname", "system node release version machine processor")  # noqa: PYI024
+    monkeypatch.setattr(platform, "uname", lambda: uname("Li'nux", "n", "6.1'); DROP TABLE genomes; --", "v", 'x"86', ""))
+    hashes = [f"{i:032x}" for i in range(5)]
+    ident = np.random.default_rng(5).random((5, 5))
+    cov = ident * 0.5
+    ident[0, 3] = cov[0, 3] = np.nan
+    with db_orm.connect_to_db(logger, tmp_path / "lit.sqlite") as session:
+        config = db_orm.db_configuration(session, "sourmash", "panib200", "0", kmersize=31, extra="scaled=1000",
+                                         create=True)
+        for h in hashes:
+            db_orm.db_genome(logger, session, tmp_path / f"{h}.fna", h, create=True, stats=(10, b"t", False),
+                             commit=False)
+        run = db_orm.add_run(session, config, "x", tmp_path, "Running", "t", None,
+                             {tmp_path / f"{h}.fna": h for h in hashes})
+        assert db_orm.insert_comparison_arrays(logger, session, config.configuration_id, hashes, hashes, ident, cov)
+        rows = session.execute(
+            "SELECT query_hash, subject_hash, configuration_id, identity, aln_length, sim_errors, cov_query,"
+            " cov_subject, uname_system, uname_release, uname_machine FROM comparisons ORDER BY comparison_id"
+        ).fetchall()
+        assert len(rows) == 25 and session.execute("SELECT COUNT(*) FROM genomes").fetchone()[0] == 5
+        for r, (q, s) in zip(rows, ((q, s) for q in range(5) for s in range(5)), strict=True):
+            want_i = None if np.isnan(ident[q, s]) else ident[q, s]
+            want_c = None if np.isnan(cov[q, s]) else cov[q, s]
+            assert r == (hashes[q], hashes[s], config.configuration_id, want_i, None, None, want_c, None,
+                         "Li'nux", "6.1'); DROP TABLE genomes; --", 'x"86')
+        # a second call is ignored row by row (INSERT OR IGNORE on the unique key)
+        assert db_orm.insert_comparison_arrays(logger, session, config.configuration_id, hashes, hashes, ident, cov)
+        assert session.execute("SELECT COUNT(*) FROM comparisons").fetchone()[0] == 25
+        run.cache_comparisons()
+        null_frame = pd.DataFrame(data=np.full((5, 5), np.nan), index=hashes, columns=hashes, dtype=float)
+        assert run.df_aln_length == run.df_sim_errors == null_frame.to_json(orient="split")
+        assert run.df_identity == pd.DataFrame(data=ident, index=hashes, columns=hashes).to_json(orient="split")
