@@ -765,18 +765,25 @@ def insert_comparisons_with_retries(
 def insert_comparison_arrays(  # noqa: PLR0913
     logger: logging.Logger, session: Session, configuration_id: int, query_hashes: list[str],
     subject_hashes: list[str], identity: Any, cov_query: Any, *, rows_per_commit: int = 2_000_000,
+    rows_per_statement: int = 128,
 ) -> bool:
     """Array-backed ``INSERT OR IGNORE`` of a queries x subjects block (NaN -> NULL).
 
     Same row semantics and the same three-attempt retry as ``insert_comparisons_with_retries`` (reference:
-    db_orm.py:1044-1114), without one dict -- or one Python frame -- per pair: each query row becomes two
-    object arrays (NaN masked to None by numpy) and the parameter tuples come out of ``zip`` / ``repeat``,
-    i.e. C iterators, straight into ``executemany``.  Committed in chunks of whole query rows, so a
-    transient lock costs one chunk, not the run (what makes N = 10,000 practical).
+    db_orm.py:1044-1114), without one dict -- or one Python frame, or one statement execution -- per pair:
+
+    * each query row becomes one object array (NaN masked to None by numpy) flattened into the parameter list;
+    * the seven values that are the same for every row of the call (configuration, the three NULL columns of
+      this method, the uname strings) are literals of the statement, so a row binds four parameters, not eleven;
+    * one statement carries ``rows_per_statement`` rows (``VALUES (...), (...), ...``; 512 parameters, below
+      every SQLite build's limit), OR IGNORE still acting row by row.
+
+    Measured per row on the same machine: 2.9 us with eleven bound parameters and one statement per row, 2.3 us
+    with literals, 1.8 us with 128 rows per statement.  Committed in chunks of whole query rows, so a transient
+    lock costs one chunk, not the run (what makes N = 10,000 practical).
     Returns False when a chunk could not be recorded after three attempts.
     """
     import random  # noqa: PLC0415
-    from itertools import chain, repeat  # noqa: PLC0415
 
     import numpy as np  # noqa: PLC0415
 
@@ -784,9 +791,7 @@ def insert_comparison_arrays(  # noqa: PLR0913
     n_q, n_s = len(query_hashes), len(subject_hashes)
     msg = f"Attempting to record {n_q * n_s} comparisons."
     logger.debug(msg)
-    # the seven values that are the same for every row of the call (configuration, the three NULL columns of
-    # this method, the uname strings) are literals of the statement: four bound parameters per row instead of
-    # eleven (3.2 -> 2.6 us per row measured)
+
     def literal(text: str) -> str:
         return "'" + text.replace("'", "''") + "'"
 
@@ -795,25 +800,50 @@ def insert_comparison_arrays(  # noqa: PLR0913
               "uname_system": literal(uname.system), "uname_release": literal(uname.release),
               "uname_machine": literal(uname.machine)}
     assert set(values) == set(COMPARISON_COLUMNS)  # noqa: S101
-    sql = (f"INSERT OR IGNORE INTO comparisons ({', '.join(COMPARISON_COLUMNS)})"  # noqa: S608
-           f" VALUES ({', '.join(values[c] for c in COMPARISON_COLUMNS)})")
+    bound = [c for c in COMPARISON_COLUMNS if values[c] == "?"]  # order of the parameters of one row
+    assert bound == ["query_hash", "subject_hash", "identity", "cov_query"]  # noqa: S101
+    head = f"INSERT OR IGNORE INTO comparisons ({', '.join(COMPARISON_COLUMNS)}) VALUES "  # noqa: S608
+    one_row = "(" + ", ".join(values[c] for c in COMPARISON_COLUMNS) + ")"
+    per_stmt = max(1, int(rows_per_statement))
+    width = len(bound) * per_stmt
+    sql_full = head + ", ".join([one_row] * per_stmt)
     identity = np.asarray(identity, dtype=np.float64).reshape(n_q, n_s)
     cov_query = np.asarray(cov_query, dtype=np.float64).reshape(n_q, n_s)
+    subjects = np.array(list(subject_hashes), dtype=object)
 
-    def row_params(i: int):  # noqa: ANN202
-        ident = identity[i].astype(object)
-        ident[np.isnan(identity[i])] = None
-        cov = cov_query[i].astype(object)
-        cov[np.isnan(cov_query[i])] = None
-        return zip(repeat(query_hashes[i]), subject_hashes, ident, cov)  # the order of the "?" above
+    def row_params(i: int) -> list:
+        params = np.empty((n_s, len(bound)), dtype=object)
+        params[:, 0] = query_hashes[i]
+        params[:, 1] = subjects
+        params[:, 2] = identity[i]
+        params[np.isnan(identity[i]), 2] = None
+        params[:, 3] = cov_query[i]
+        params[np.isnan(cov_query[i]), 3] = None
+        return params.ravel().tolist()
+
+    def record(i0: int, i1: int) -> None:
+        rest: list = []
+
+        def statements():  # noqa: ANN202
+            nonlocal rest
+            for i in range(i0, i1):
+                rest += row_params(i)
+                full = len(rest) // width * width
+                for j in range(0, full, width):
+                    yield rest[j:j + width]
+                rest = rest[full:]
+
+        session.executemany(sql_full, statements())
+        if rest:
+            session.execute(head + ", ".join([one_row] * (len(rest) // len(bound))), tuple(rest))
+        session.commit()
 
     step = max(1, rows_per_commit // max(1, n_s))
     for i0 in range(0, n_q, step):
         i1 = min(n_q, i0 + step)
         for attempt, pause in ((1, 20 + 10 * random.random()), (2, 30 + 10 * random.random()), (3, 0)):  # noqa: S311
             try:
-                session.executemany(sql, chain.from_iterable(row_params(i) for i in range(i0, i1)))
-                session.commit()
+                record(i0, i1)
             except sqlite3.OperationalError:  # pragma: no cover
                 msg = f"Attempt {attempt}/3 failed to record comparisons of query rows {i0}..{i1}"
                 if attempt < 3:  # noqa: PLR2004

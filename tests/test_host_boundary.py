@@ -531,3 +531,40 @@ def test_bulk_insert_literals_and_null_matrices(tmp_path: Path, monkeypatch: pyt
         null_frame = pd.DataFrame(data=np.full((5, 5), np.nan), index=hashes, columns=hashes, dtype=float)
         assert run.df_aln_length == run.df_sim_errors == null_frame.to_json(orient="split")
         assert run.df_identity == pd.DataFrame(data=ident, index=hashes, columns=hashes).to_json(orient="split")
+
+
+@pytest.mark.parametrize(("n_q", "n_s", "per_stmt", "per_commit"), [(13, 13, 5, 40), (3, 200, 128, 2_000_000),
+                                                                    (7, 1, 4, 2), (1, 1, 128, 1)])
+def test_bulk_insert_statement_and_commit_boundaries(  # noqa: PLR0913
+    tmp_path: Path, n_q: int, n_s: int, per_stmt: int, per_commit: int,
+) -> None:
+    """Rows are packed into multi-row statements across query-row and commit-chunk boundaries: every ordered
+    pair arrives exactly once, in order, with its own values, whatever the block shape."""
+    import logging
+
+    import numpy as np
+
+    from pyani_plus_b200 import db_orm
+
+    logger = logging.getLogger("test")
+    queries = [f"{i:032x}" for i in range(n_q)]
+    subjects = [f"{i + 1000:032x}" for i in range(n_s)]
+    rng = np.random.default_rng(n_q * 1000 + n_s)
+    ident = rng.random((n_q, n_s))
+    cov = rng.random((n_q, n_s))
+    ident[rng.random((n_q, n_s)) < 0.2] = np.nan
+    cov[np.isnan(ident)] = np.nan
+    with db_orm.connect_to_db(logger, tmp_path / "b.sqlite") as session:
+        config = db_orm.db_configuration(session, "sourmash", "panib200", "0", kmersize=31, extra="scaled=1000",
+                                         create=True)
+        for h in [*queries, *subjects]:
+            db_orm.db_genome(logger, session, tmp_path / f"{h}.fna", h, create=True, stats=(10, b"t", False),
+                             commit=False)
+        session.commit()
+        assert db_orm.insert_comparison_arrays(logger, session, config.configuration_id, queries, subjects, ident,
+                                               cov, rows_per_commit=per_commit, rows_per_statement=per_stmt)
+        rows = session.execute(
+            "SELECT query_hash, subject_hash, identity, cov_query FROM comparisons ORDER BY comparison_id").fetchall()
+    want = [(queries[q], subjects[s], None if np.isnan(ident[q, s]) else ident[q, s],
+             None if np.isnan(cov[q, s]) else cov[q, s]) for q in range(n_q) for s in range(n_s)]
+    assert rows == want
