@@ -585,14 +585,26 @@ def compute_sourmash_bulk(logger: logging.Logger, session: Session, run: db_orm.
 
 
 def missing_block(run: db_orm.Run) -> tuple[set[str], set[str]]:
-    """The smallest queries x subjects block that covers every comparison the run still lacks."""
+    """The smallest queries x subjects block that covers every comparison the run still lacks.
+
+    Counted inside SQLite (one GROUP BY over the run's comparisons), then only the subjects that are short of a
+    full column are looked at row by row: resuming a run of 10,000 genomes does not build 10^8 Python objects.
+    """
     hashes = sorted(link.genome_hash for link in run.fasta_hashes)
-    have: dict[str, set[str]] = {h: set() for h in hashes}
-    for comp in run.comparisons():
-        have[comp.subject_hash].add(comp.query_hash)
     everyone = set(hashes)
-    subjects = {s for s, qs in have.items() if len(qs) < len(hashes)}
-    queries = set().union(*(everyone - have[s] for s in subjects)) if subjects else set()
+    session = run._session  # noqa: SLF001
+    params = (run.configuration_id, run.run_id, run.run_id)
+    have = dict(session.execute("SELECT comparisons.subject_hash, COUNT(*)" + db_orm._RUN_JOIN  # noqa: SLF001
+                                + " GROUP BY comparisons.subject_hash", params).fetchall())
+    subjects = {h for h in hashes if have.get(h, 0) < len(hashes)}
+    queries: set[str] = set()
+    for subject in subjects:
+        if len(queries) == len(everyone):
+            break
+        present = {row[0] for row in session.execute(
+            "SELECT comparisons.query_hash" + db_orm._RUN_JOIN + " AND comparisons.subject_hash = ?",  # noqa: SLF001
+            (*params, subject))} if have.get(subject, 0) else set()
+        queries |= everyone - present
     return queries, subjects
 
 

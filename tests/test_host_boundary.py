@@ -568,3 +568,43 @@ def test_bulk_insert_statement_and_commit_boundaries(  # noqa: PLR0913
     want = [(queries[q], subjects[s], None if np.isnan(ident[q, s]) else ident[q, s],
              None if np.isnan(cov[q, s]) else cov[q, s]) for q in range(n_q) for s in range(n_s)]
     assert rows == want
+
+
+def test_missing_block_counts_in_sql(tmp_path: Path) -> None:
+    """``missing_block`` (resume: reference private_cli.py:879-898 computes only what a column lacks) equals the
+    row-by-row definition on partially filled runs, incl. comparisons that belong to genomes outside the run."""
+    import logging
+
+    import numpy as np
+
+    from pyani_plus_b200 import db_orm, private_cli
+
+    logger = logging.getLogger("test")
+    rng = np.random.default_rng(11)
+    hashes = [f"{i:032x}" for i in range(9)]
+    outsider = "f" * 32
+    for case in range(6):
+        with db_orm.connect_to_db(logger, tmp_path / f"m{case}.sqlite") as session:
+            config = db_orm.db_configuration(session, "sourmash", "panib200", "0", kmersize=31,
+                                             extra="scaled=1000", create=True)
+            for h in [*hashes, outsider]:
+                db_orm.db_genome(logger, session, tmp_path / f"{h}.fna", h, create=True, stats=(10, b"t", False),
+                                 commit=False)
+            run = db_orm.add_run(session, config, "x", tmp_path, "Running", "t", None,
+                                 {tmp_path / f"{h}.fna": h for h in hashes})
+            keep = rng.random((9, 9)) < (0.0, 0.5, 0.9, 1.0, 0.97, 0.2)[case]
+            if case == 4:
+                keep[:, 3] = False  # one subject without any comparison
+            for q in range(9):
+                present = [hashes[s] for s in range(9) if keep[q, s]]
+                if present:
+                    vals = np.full(len(present), 0.5)
+                    db_orm.insert_comparison_arrays(logger, session, config.configuration_id, [hashes[q]], present,
+                                                    vals, vals)
+            # rows of a genome that is not part of the run must not count
+            db_orm.insert_comparison_arrays(logger, session, config.configuration_id, [outsider], hashes,
+                                            np.full(9, 0.1), np.full(9, 0.1))
+            queries, subjects = private_cli.missing_block(run)
+            want_s = {hashes[s] for s in range(9) if not keep[:, s].all()}
+            want_q = {hashes[q] for s in range(9) for q in range(9) if not keep[q, s]}
+            assert (queries, subjects) == (want_q, want_s), case
