@@ -408,6 +408,36 @@ class Run:
         return RunComparisons(self)
 
     # ---- cached matrices ----------------------------------------------------------------------
+    def _scatter_comparisons(self, hashes: list[str], columns: tuple[str, ...]) -> "tuple[list[np.ndarray], int]":  # noqa: UP037
+        """The run's comparisons as N x N float matrices (NaN where a row is missing or NULL), one per column, and
+        the number of rows seen.  Row / column positions are resolved inside SQLite (a temporary md5 -> index
+        table joined twice) and the rows arrive in batches that numpy scatters: no Python work per pair."""
+        import numpy as np  # noqa: PLC0415
+
+        size = len(hashes)
+        out = [np.full([size, size], np.nan, float) for _ in columns]
+        session = self._session
+        session.execute("CREATE TEMP TABLE IF NOT EXISTS panib_matrix_index (genome_hash VARCHAR PRIMARY KEY, pos INTEGER)")
+        session.execute("DELETE FROM panib_matrix_index")
+        session.executemany("INSERT INTO panib_matrix_index VALUES (?, ?)", list(zip(hashes, range(size), strict=True)))
+        cursor = session.execute(
+            "SELECT q.pos, s.pos, " + ", ".join(f"comparisons.{c}" for c in columns) + " FROM comparisons"
+            " JOIN panib_matrix_index AS q ON comparisons.query_hash = q.genome_hash"
+            " JOIN panib_matrix_index AS s ON comparisons.subject_hash = s.genome_hash"
+            " WHERE comparisons.configuration_id = ?", (self.configuration_id,))
+        seen = 0
+        while True:
+            rows = cursor.fetchmany(200_000)
+            if not rows:
+                break
+            block = np.array(rows, dtype=float)  # None -> nan
+            qi, si = block[:, 0].astype(np.intp), block[:, 1].astype(np.intp)
+            for m, values in zip(out, block[:, 2:].T, strict=True):
+                m[qi, si] = values
+            seen += len(rows)
+        session.execute("DELETE FROM panib_matrix_index")
+        return out, seen
+
     def cache_comparisons(self, *, computed: tuple | None = None) -> None:
         """Collect the N x N matrices and cache them as pandas "split" JSON (reference: db_orm.py:393-466).
 
@@ -419,7 +449,6 @@ class Run:
         import pandas as pd  # noqa: PLC0415
 
         hashes = sorted(a.genome_hash for a in self.fasta_hashes)
-        where = {h: i for i, h in enumerate(hashes)}
         size = len(hashes)
         if size * size * MATRIX_JSON_BYTES_PER_CELL > MATRIX_CACHE_MAX_BYTES:
             # SQLite refuses strings above 10^9 bytes (SQLITE_MAX_LENGTH), and the reference's cache format is
@@ -436,16 +465,8 @@ class Run:
             identity[:] = computed[1]
             cov_query[:] = computed[2]
         elif self._session is not None:
-            sql = ("SELECT comparisons.query_hash, comparisons.subject_hash, comparisons.identity,"
-                   " comparisons.cov_query, comparisons.aln_length, comparisons.sim_errors" + _RUN_JOIN)
-            for q, s, idn, cov, aln, sim in self._session.execute(
-                sql, (self.configuration_id, self.run_id, self.run_id)
-            ):
-                row, col = where[q], where[s]
-                identity[row, col] = np.nan if idn is None else idn
-                cov_query[row, col] = np.nan if cov is None else cov
-                aln_length[row, col] = np.nan if aln is None else aln
-                sim_errors[row, col] = np.nan if sim is None else sim
+            (identity, cov_query, aln_length, sim_errors), _ = self._scatter_comparisons(
+                hashes, ("identity", "cov_query", "aln_length", "sim_errors"))
 
         def as_json(data: "np.ndarray") -> str:  # noqa: UP037
             if size and np.isnan(data).all():
@@ -484,18 +505,8 @@ class Run:
         size = len(hashes)
         if size * size * MATRIX_JSON_BYTES_PER_CELL <= MATRIX_CACHE_MAX_BYTES:
             return None
-        where = {h: i for i, h in enumerate(hashes)}
         cols = ("identity", "cov_query") if column == "hadamard" else (column,)
-        out = [np.full([size, size], np.nan, float) for _ in cols]
-        sql = ("SELECT comparisons.query_hash, comparisons.subject_hash, "
-               + ", ".join(f"comparisons.{c}" for c in cols) + _RUN_JOIN)
-        seen = 0
-        for q, s, *vals in self._session.execute(sql, (self.configuration_id, self.run_id, self.run_id)):
-            row, col = where[q], where[s]
-            for m, v in zip(out, vals, strict=True):
-                if v is not None:
-                    m[row, col] = v
-            seen += 1
+        out, seen = self._scatter_comparisons(hashes, cols)
         if seen != size * size:
             return None
         data = out[0] * out[1] if column == "hadamard" else out[0]
