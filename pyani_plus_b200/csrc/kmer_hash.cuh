@@ -639,7 +639,16 @@ struct KmerStep {
 #endif
 #else
             if (p0.prefilter(hc)) {  // ~1/scaled of the k-mers; validity is tested on this rare path only
-                if (vmask & (1u << J)) emit(p0);
+#if defined(__CUDA_ARCH__)
+                // Left in the source order, ptxas merges the validity test into the hot predicate (one LOP3 per
+                // k-mer).  The thread's mask therefore waits in its own scratch (reverse position 0, which no
+                // k-mer reads; stored by hash_thread_kmers) behind a volatile load that cannot be hoisted.
+                uint32_t vm;
+                asm volatile("ld.volatile.shared.u32 %0, [%1+%2];" : "=r"(vm) : "r"(fw), "n"(kBlkPairs * ROW));
+#else
+                const uint32_t vm = vmask;
+#endif
+                if (vm & (1u << J)) emit(p0);
             }
 #if PANIB_K1_GROUP == 2
             if (p1.prefilter(hc)) {
@@ -687,6 +696,10 @@ PANIB_HD void hash_thread_kmers(const uint32_t *sp, const uint32_t *rcp, const u
             Xr[w] = shf_r(srcr[w], srcr[w + 1], sr);
         }
     }
+#if defined(__CUDA_ARCH__)
+    // the validity mask for the rare path (KmerStep::run): this thread's reverse position 0, free during phase B
+    asm volatile("st.volatile.shared.u32 [%0+%1], %2;" ::"r"(scr_base(blk)), "n"(kBlkPairs * 2 * kThreadsK1 * 4), "r"(vmask));
+#endif
     KmerStep<K, 0, typename std::remove_reference<Emit>::type, S42>::run(X, Xr, scr_base(blk), vmask, hc, emit);
 }
 

@@ -324,6 +324,12 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
     int64_t next = ticket ? s_next : tile + gridDim.x;
     const int u = tid >> 2, a = tid & 3;
     const EmitToTable emit{&s_slot, max_hash, status, surv, &s_nsurv};
+    // The prefilter threshold as a COMPUTED uniform value (blockIdx.y is always 0: the grid is 1-D): ptxas keeps
+    // that in a uniform register, whereas it re-loads a plain kernel parameter from the constant bank for every
+    // k-mer (one LDCU per k-mer less; with the validity test on the rare path 97 -> 95 instructions per k-mer in
+    // the hot loop, measured +1.0 % at configs[1] and configs[2])
+    HashConsts hc2 = hc;
+    hc2.thr ^= blockIdx.y;
     int g = 0;
     for (int it = 0; tile < n_tiles; ++it) {
         const int cur = it & 1;
@@ -355,7 +361,7 @@ sketch_hash_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restri
         const bool dirty = __syncthreads_or(mw != 0u) != 0;
         // phase B
         const uint32_t vmask = dirty ? thread_valid_mask<K>(sm[cur], u, a) : 0xFFFFu;
-        hash_thread_kmers<K, S42>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc, emit);
+        hash_thread_kmers<K, S42>(sp, rcp, scratch + 2 * tid, u, a, vmask, hc2, emit);
         // read by everyone after the next barrier; the last read of the old value was before the barrier above
         if (tid == 0) s_next = ticket ? (next < n_tiles ? dyn_base + drawn : n_tiles) : next + gridDim.x;
         tile = next;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # End-of-round check on one B200, most important first (every step has its own timeout):
-#   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh final3'
+#   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh final3 [profile]'
 # 1 GPU parity suite   2 smoke()   3 bench.py, default workload (configs[2])   4 the reference arm
 # 5 configs[1] and configs[4] bench lines   6 drop-in CLI wall time at 1,000 genomes
 # Everything lands in gpurun_out/<tag>_*; copy what is to be judged into profiles/.
@@ -15,6 +15,13 @@ timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; e
 tail -3 $OUT/${TAG}_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_smoke.log
 tail -2 $OUT/${TAG}_smoke.log
+# optional second argument "profile": re-take the ncu captures of the bench step first (a kernel source changed)
+if [ "${2:-}" = profile ]; then
+  bash tools/profile_r2.sh r02 config3 > $OUT/${TAG}_profile.log 2>&1
+  python tools/ncu_to_json.py r02 config3 k1=$OUT/prof_k1_r02.ncu-rep k2_index=$OUT/prof_k2idx_r02.ncu-rep \
+      k2_probe=$OUT/prof_k2probe_r02.ncu-rep --sha $OUT/source_sha_r02.txt > $OUT/${TAG}_ncu_to_json.log 2>&1
+  cp profiles/ncu_r02.json $OUT/ncu_r02.json   # the bench lines below then carry the measured fields
+fi
 timeout 600 python bench.py > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err; echo "rc=$?" >> $OUT/${TAG}_bench_default.err
 timeout 600 python bench.py --impl reference > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "rc=$?" >> $OUT/${TAG}_bench_reference.err
 for w in config2 config5; do
