@@ -106,3 +106,47 @@ def test_stream_layout() -> None:
     assert (buf[5 * 4096:] == ord("N")).all()
     with pytest.raises(ValueError, match="wrong shape"):
         stream.fill_ascii_stream(buf[:-1], toff, [])
+
+
+@pytest.mark.parametrize(("k", "scaled", "seed"), [(31, 3, 1), (31, 1, 2), (21, 2, 3), (32, 4, 4), (15, 2, 5), (16, 1, 6),
+                                                   (7, 1, 7)])
+def test_thread_logic_fuzz(emu: ctypes.CDLL, k: int, scaled: int, seed: int) -> None:
+    """Seeded random genomes built to sit on every seam of the kernel's geometry: record and N-run boundaries at
+    random offsets (inside a thread's 64-base block, across 16-base packed words, across 4096-base tiles),
+    lower case, IUPAC letters, runs shorter and longer than k, records shorter than k, palindromic stretches
+    (forward == reverse complement for even k), low-complexity repeats (duplicate hashes).  A small ``scaled``
+    keeps every second to every hash, so a single wrong canonical choice or window shows up."""
+    rng = np.random.default_rng(20261017 + seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+
+    def random_record(length: int) -> bytes:
+        seq = acgt[rng.integers(0, 4, length)].copy()
+        for _ in range(int(rng.integers(0, 4))):  # N runs / IUPAC letters
+            at, run = int(rng.integers(0, max(1, length))), int(rng.choice([1, 2, k - 1, k, k + 1, 40, 70]))
+            seq[at: at + run] = rng.choice(np.frombuffer(b"NRYKMnx-", dtype=np.uint8))
+        if length > 4 * k and rng.random() < 0.5:  # a reverse-complement palindrome
+            at = int(rng.integers(0, length - 2 * k))
+            half = seq[at: at + k].copy()
+            if all(int(c) in comp for c in half):
+                seq[at + k: at + 2 * k] = np.array([comp[int(c)] for c in half[::-1]], dtype=np.uint8)
+        if length > 200 and rng.random() < 0.5:  # a tandem repeat: the same k-mers again and again
+            at, unit = int(rng.integers(0, length - 150)), int(rng.choice([1, 2, 3, 5]))
+            seq[at: at + 120] = np.resize(seq[at: at + unit], 120)
+        if rng.random() < 0.3:
+            lo = int(rng.integers(0, max(1, length)))
+            seq[lo: lo + 50] = np.frombuffer(seq[lo: lo + 50].tobytes().lower(), dtype=np.uint8)
+        return seq.tobytes()
+
+    genomes = []
+    for _ in range(10):
+        n_rec = int(rng.choice([1, 1, 2, 3, 6]))
+        recs = []
+        for _ in range(n_rec):
+            length = int(rng.choice([0, 1, k - 1, k, k + 1, 63, 64, 65, 4095, 4096, 4097,
+                                     int(rng.integers(100, 9000))]))
+            recs.append(random_record(length))
+        genomes.append(recs)
+    got = emu_sketch(emu, genomes, k, scaled)
+    for g, recs in enumerate(genomes):
+        assert got[g].tolist() == oracle.sketch_records(recs, k, scaled).tolist(), (k, seed, g, [len(r) for r in recs])
