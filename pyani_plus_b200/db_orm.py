@@ -315,6 +315,20 @@ class RunComparisons:
         sql, params = self._where()
         return int(self.run._session.execute("SELECT COUNT(*)" + sql, params).fetchone()[0])  # noqa: SLF001
 
+    def null_count(self) -> int:
+        """Comparisons without an identity (no common hash), counted inside SQLite."""
+        sql, params = self._where()
+        return int(self.run._session.execute(  # noqa: SLF001
+            "SELECT COUNT(*) - COUNT(comparisons.identity)" + sql, params).fetchone()[0])
+
+    def values(self):  # noqa: ANN201
+        """(query_hash, subject_hash, identity, cov_query) of every comparison, ordered by query then subject,
+        streamed from SQLite (no row objects: a run of 10,000 genomes has 10^8 of them)."""
+        sql, params = self._where()
+        return self.run._session.execute(  # noqa: SLF001
+            "SELECT comparisons.query_hash, comparisons.subject_hash, comparisons.identity, comparisons.cov_query"
+            + sql + " ORDER BY comparisons.query_hash, comparisons.subject_hash", params)
+
     def where_subject(self, subject_hash: str) -> "RunComparisons":  # noqa: UP037
         return RunComparisons(self.run, subject_hash)
 

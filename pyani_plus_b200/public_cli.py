@@ -424,11 +424,11 @@ def list_runs(database: REQ_DB) -> int:
         for run in runs:
             conf = run.configuration
             n = run.genomes.count()
-            rows = list(run.comparisons())
-            null = sum(1 for c in rows if c.identity is None)
+            have = run.comparisons().count()  # counted by SQLite: a large run has 10^8 rows
+            null = run.comparisons().null_count()
             table.add_row(
-                str(run.run_id), str(run.date.date()), conf.method, str(len(rows) - null), str(null),
-                str(n**2 - len(rows)), f"{n**2}={n}²", run.status, run.name,
+                str(run.run_id), str(run.date.date()), conf.method, str(have - null), str(null),
+                str(n**2 - have), f"{n**2}={n}²", run.status, run.name,
             )
     Console().print(table)
     return 0
@@ -464,11 +464,10 @@ def export_run(  # noqa: PLR0913
         mapping = {a.genome_hash: a.fasta_filename for a in run.fasta_hashes}
         with (outdir / f"{method}_run_{run.run_id}.tsv").open("w") as handle:
             handle.write("#Query\tSubject\tIdentity\tQuery-Cov\n")
-            for comp in sorted(run.comparisons(), key=lambda c: (c.query_hash, c.subject_hash)):
+            for query, subject, identity, cov_query in run.comparisons().values():  # ordered and streamed by SQLite
                 handle.write(
-                    f"{mapping[comp.query_hash]}\t{mapping[comp.subject_hash]}\t"
-                    f"{'' if comp.identity is None else comp.identity}\t"
-                    f"{'' if comp.cov_query is None else comp.cov_query}\n"
+                    f"{mapping[query]}\t{mapping[subject]}\t"
+                    f"{'' if identity is None else identity}\t{'' if cov_query is None else cov_query}\n"
                 )
     msg = f"Wrote matrices to {outdir}/{method}_*.tsv"
     logger.info(msg)
