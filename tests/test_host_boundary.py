@@ -608,3 +608,25 @@ def test_missing_block_counts_in_sql(tmp_path: Path) -> None:
             want_s = {hashes[s] for s in range(9) if not keep[:, s].all()}
             want_q = {hashes[q] for s in range(9) for q in range(9) if not keep[q, s]}
             assert (queries, subjects) == (want_q, want_s), case
+
+
+def test_md5_failure_modes_and_logger_flag(golden: Path, tmp_path: Path) -> None:
+    """Reference tests/test_utils.py: test_md5_str / test_md5_path :36-49 (gzip, str and Path), test_md5_invalid
+    :52-63 (missing file, broken symlink), test_setup_logger_dynamic :103-110; plus ``fasta_file_stats``, the
+    one-pass form the CLI uses, which must fail the same way."""
+    from pyani_plus_b200 import setup_logger
+
+    gz = golden / "bacterial_example" / "NC_002696.fasta.gz"
+    assert utils.file_md5sum(str(gz)) == utils.file_md5sum(gz) == "f19cb07198a41a4406a22b2f57a6b5e7"
+    md5, total, title, is_gzip = utils.fasta_file_stats(gz)
+    assert (md5, total, is_gzip) == ("f19cb07198a41a4406a22b2f57a6b5e7", 4016947, True)
+    assert title is not None and title.startswith(b"NC_002696")
+    bad_link = tmp_path / "bad-link.fasta"
+    bad_link.symlink_to("/does/not/exist.fasta")
+    for fn in (utils.file_md5sum, utils.fasta_file_stats):
+        with pytest.raises(ValueError, match=r"Input /does/not/exist\.txt not found"):
+            fn("/does/not/exist.txt")
+        with pytest.raises(ValueError, match=r"Input .*/bad-link\.fasta is a broken symlink"):
+            fn(bad_link)
+    with pytest.raises(SystemExit, match="ERROR: Internal flag value for dynamic log setting unresolved"):
+        setup_logger(Path("--"))
