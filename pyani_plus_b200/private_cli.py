@@ -266,18 +266,29 @@ def import_comparisons(
     json: Annotated[list[Path], typer.Argument(help="JSON file(s) of comparisons", show_default=False)],
     *,
     debug: OPT_DEBUG = False,
+    log: OPT_LOG = NO_PATH,
 ) -> int:
-    """Import JSON file(s) of pairwise comparisons into the database."""
-    logger = setup_logger(None, terminal_level=logging.DEBUG if debug else logging.INFO)
+    """Import JSON file(s) of pairwise comparisons into the database.
+
+    The database must already hold the matching configuration (log-configuration) and the genomes (log-genome);
+    each file carries one configuration, one uname and any number of comparisons (reference
+    private_cli.py:618-674: what its workflow calls while a run progresses).
+    """
+    logger = setup_logger(log, terminal_level=logging.DEBUG if debug else logging.ERROR)
     if database != ":memory:" and not Path(database).is_file():
         msg = f"Database '{database}' does not exist"
-        log_sys_exit(logger, msg)
-    total = 0
-    with db_orm.connect_to_db(logger, database) as session:
-        for filename in json:
-            total += import_json_comparisons(logger, session, filename)
-    msg = f"Imported {total} from {len(json)} JSON files"
+        sys.exit(msg)
+    msg = f"Logging comparison to '{database}'"
     logger.info(msg)
+    with db_orm.connect_to_db(logger, database) as session:
+        for table, what in (("configurations", "configurations"), ("genomes", "genomes")):
+            if session.execute(f"SELECT COUNT(*) FROM {table}").fetchone()[0] == 0:  # noqa: S608
+                msg = f"{database} does not contain any {what}"
+                log_sys_exit(logger, msg)
+        for filename in json:
+            count = import_json_comparisons(logger, session, filename)
+            msg = f"Imported {count} from '{filename}'"
+            logger.info(msg)
     return 0
 
 
