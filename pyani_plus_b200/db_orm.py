@@ -321,12 +321,17 @@ class RunComparisons:
         return int(self.run._session.execute(  # noqa: SLF001
             "SELECT COUNT(*) - COUNT(comparisons.identity)" + sql, params).fetchone()[0])
 
-    def values(self):  # noqa: ANN201
-        """(query_hash, subject_hash, identity, cov_query) of every comparison, ordered by query then subject,
-        streamed from SQLite (no row objects: a run of 10,000 genomes has 10^8 of them)."""
+    def values(self, columns: tuple[str, ...] = ("identity", "cov_query")):  # noqa: ANN201
+        """(query_hash, subject_hash, *columns) of every comparison, ordered by query then subject, streamed from
+        SQLite (no row objects: a run of 10,000 genomes has 10^8 of them)."""
+        unknown = set(columns) - set(COMPARISON_COLUMNS)
+        if unknown:
+            msg = f"not comparison columns: {sorted(unknown)}"
+            raise ValueError(msg)
         sql, params = self._where()
         return self.run._session.execute(  # noqa: SLF001
-            "SELECT comparisons.query_hash, comparisons.subject_hash, comparisons.identity, comparisons.cov_query"
+            "SELECT comparisons.query_hash, comparisons.subject_hash"
+            + "".join(f", comparisons.{c}" for c in columns)
             + sql + " ORDER BY comparisons.query_hash, comparisons.subject_hash", params)
 
     def where_subject(self, subject_hash: str) -> "RunComparisons":  # noqa: UP037

@@ -419,8 +419,15 @@ def list_runs(database: REQ_DB) -> int:
     with db_orm.connect_to_db(logger, database) as session:
         runs = session.runs()
         table = Table(title=f"{len(runs)} analysis runs in {database}", row_styles=["dim", ""])
+        from rich.text import Text  # noqa: PLC0415
+
         for col in ("ID", "Date", "Method", "Done", "Null", "Miss", "Total", "Status", "Name"):
-            table.add_column(col)
+            if col == "ID":
+                table.add_column(col, justify="right", no_wrap=True)
+            elif col in ("Done", "Null", "Miss", "Total"):  # numbers right-aligned under left-aligned headings
+                table.add_column(Text(col, justify="left"), justify="right", no_wrap=True)
+            else:
+                table.add_column(col)
         for run in runs:
             conf = run.configuration
             n = run.genomes.count()
@@ -441,34 +448,67 @@ def export_run(  # noqa: PLR0913
                                          show_default=False)],
     run_id: OPT_RUN_ID = None,
     label: Annotated[str, typer.Option(help="How to label the genomes: md5, filename or stem.")] = "stem",
+    log: OPT_LOG = Path("-"),
+    *,
+    debug: OPT_DEBUG = False,
 ) -> int:
-    """Export the run's matrices (identity, query coverage, hadamard, tANI) and the long-form table as TSV."""
-    logger = setup_logger(None)
+    """Export any single run: the long-form table ``<method>_run_<run-id>.tsv`` (every comparison with all its
+    properties, NA for NULL) and, for a complete run, the matrices ``<method>_<property>.tsv``.
+
+    As the reference's command (public_cli.py:974-1091): a partial run gets its long-form table and then an
+    error instead of matrices; an empty run is an error.  Rows are streamed from SQLite in (query, subject) order.
+    """
+    from math import log as math_log  # noqa: PLC0415
+
+    logger = setup_logger(log, terminal_level=logging.DEBUG if debug else logging.INFO)
     if database == ":memory:" or not Path(database).is_file():
         msg = f"Database {database} does not exist"
         log_sys_exit(logger, msg)
-    outdir.mkdir(parents=True, exist_ok=True)
+    if not outdir.is_dir():
+        msg = f"Output directory {outdir} does not exist, making it."
+        logger.warning(msg)
+        outdir.mkdir(parents=True)
     with db_orm.connect_to_db(logger, database) as session:
         run = db_orm.load_run(session, run_id, check_empty=True)
+        if run_id is None:
+            run_id = run.run_id
+            msg = f"Exporting run-id {run_id}"
+            logger.info(msg)
         method = run.configuration.method
-        if run.identities is None:
-            run.cache_comparisons()
-            session.commit()
-        for stem, matrix in (("identity", run.identities), ("query_cov", run.cov_query),
-                             ("hadamard", run.hadamard), ("tANI", run.tani)):
+        if label == "md5":
+            names = {a.genome_hash: a.genome_hash for a in run.fasta_hashes}
+        elif label == "filename":
+            names = {a.genome_hash: a.fasta_filename for a in run.fasta_hashes}
+        else:
+            names = {a.genome_hash: db_orm.filename_stem(a.fasta_filename) for a in run.fasta_hashes}
+
+        def cell(value: float | None) -> str:
+            return "NA" if value is None else str(value)
+
+        long_name = f"{method}_run_{run_id}.tsv"
+        with (outdir / long_name).open("w") as handle:
+            handle.write("#Query\tSubject\tIdentity\tQuery-Cov\tSubject-Cov\tHadamard\ttANI\tAlign-Len\tSim-Errors\n")
+            for query, subject, identity, cov_query, cov_subject, aln_length, sim_errors in run.comparisons().values(
+                    ("identity", "cov_query", "cov_subject", "aln_length", "sim_errors")):
+                hadamard = None if identity is None or cov_query is None else identity * cov_query
+                tani = None if hadamard is None else -math_log(hadamard)
+                handle.write("\t".join((names[query], names[subject], cell(identity), cell(cov_query), cell(cov_subject),
+                                        cell(hadamard), cell(tani), cell(aln_length), cell(sim_errors))) + "\n")
+        msg = f"Wrote long-form to {outdir}/{long_name}"
+        logger.info(msg)
+
+        run = db_orm.load_run(session, run_id, check_complete=True)  # a partial run stops here
+        for matrix, filename in ((run.identities, f"{method}_identity.tsv"),
+                                 (run.aln_length, f"{method}_aln_lengths.tsv"),
+                                 (run.sim_errors, f"{method}_sim_errors.tsv"),
+                                 (run.cov_query, f"{method}_query_cov.tsv"),
+                                 (run.hadamard, f"{method}_hadamard.tsv"),
+                                 (run.tani, f"{method}_tANI.tsv")):
             try:
                 matrix = run.relabelled_matrix(matrix, label)
             except ValueError as err:
                 log_sys_exit(logger, str(err))
-            matrix.to_csv(outdir / f"{method}_{stem}.tsv", sep="\t")
-        mapping = {a.genome_hash: a.fasta_filename for a in run.fasta_hashes}
-        with (outdir / f"{method}_run_{run.run_id}.tsv").open("w") as handle:
-            handle.write("#Query\tSubject\tIdentity\tQuery-Cov\n")
-            for query, subject, identity, cov_query in run.comparisons().values():  # ordered and streamed by SQLite
-                handle.write(
-                    f"{mapping[query]}\t{mapping[subject]}\t"
-                    f"{'' if identity is None else identity}\t{'' if cov_query is None else cov_query}\n"
-                )
+            matrix.to_csv(outdir / filename, sep="\t")
     msg = f"Wrote matrices to {outdir}/{method}_*.tsv"
     logger.info(msg)
     return 0

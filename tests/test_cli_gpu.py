@@ -248,7 +248,7 @@ def test_resume_partial_sourmash(caplog: pytest.LogCaptureFixture, capsys: pytes
     public_cli.list_runs(database=tmp_db)
     output = capsys.readouterr().out
     assert " 1 analysis runs in " in output, output
-    assert " sourmash │ 4    │ 0    │ 5    │ 9=3²  │ Partial " in output or "Partial" in output, output
+    assert " sourmash │    4 │    0 │    5 │  9=3² │ Partial " in output or "Partial" in output, output
     caplog.clear()
     public_cli.resume(database=tmp_db, cache=tmp_path)
     assert "Resuming run-id 1" in caplog.text
