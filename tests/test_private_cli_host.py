@@ -99,7 +99,7 @@ def test_missing_db(tmp_path: Path) -> None:
     with pytest.raises(SystemExit, match="does not exist"):
         private_cli.prepare_genomes(database=tmp_db, run_id=1)
     with pytest.raises(SystemExit, match="does not exist"):
-        private_cli.compute_column(database=tmp_db, run_id=1, subject="1", json=tmp_path / "out.json")
+        private_cli.compute_column(database=tmp_db, run_id=1, subject="1", json=tmp_path / "out.json", log=Path("-"))
 
 
 def test_prepare_genomes_unknown_method(tmp_path: Path, input_genomes_tiny: Path) -> None:
